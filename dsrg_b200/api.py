@@ -1,0 +1,214 @@
+"""Python host side of the C ABI: thin wrappers, no compute.
+
+`Engine` mirrors dsrg_engine.  Device arrays are torch CUDA tensors used purely as memory
+containers (``data_ptr()``); host arrays are numpy.  Every method maps 1:1 onto an entry point of
+include/dsrg_b200.h -- see that header for the reference interface each one replaces.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, CrfParams, DsrgError, check  # noqa: F401
+
+
+def crf_params(scale_factor=1.0, color_factor=13, maxiter=10):
+    """The pairwise parameters CRF() uses (CRF/krahenbuhl2013/CRF.py:31-32)."""
+    p = CrfParams()
+    _lib.lib().dsrg_crf_params_default(C.byref(p), float(scale_factor), float(color_factor), int(maxiter))
+    return p
+
+
+def _dptr(t):
+    """Device pointer of a contiguous torch CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def _hptr(a, dtype):
+    if a is None:
+        return None
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("expected a C-contiguous numpy array of dtype %s" % np.dtype(dtype))
+    return C.c_void_p(a.ctypes.data)
+
+
+def _stream(stream):
+    if stream is None:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over pinned host memory from dsrg_host_alloc (freed with the array)."""
+    L = _lib.lib()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = L.dsrg_host_alloc(max(n, 16))
+    if not p:
+        raise DsrgError(_lib.E_NOMEM, L.dsrg_last_error().decode())
+    buf = (C.c_char * max(n, 16)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.ctypes.data] = (p, buf)
+    return arr
+
+
+_PINNED = {}
+
+
+class Engine(object):
+    """dsrg_engine: all device buffers for batches of up to ``max_batch`` H x W x M problems."""
+
+    def __init__(self, max_batch, H, W, M=21, device=0):
+        self._L = _lib.lib()
+        self.max_batch, self.H, self.W, self.M, self.device = int(max_batch), int(H), int(W), int(M), int(device)
+        self.h = self._L.dsrg_engine_create(self.device, self.max_batch, self.H, self.W, self.M)
+        if not self.h:
+            raise DsrgError(_lib.E_CUDA, self._L.dsrg_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.dsrg_engine_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def device_bytes(self):
+        return self._L.dsrg_engine_device_bytes(self.h)
+
+    def take_launch_count(self):
+        return int(self._L.dsrg_engine_take_launch_count(self.h))
+
+    # ---- device entry points (torch tensors as containers) ----
+    def crf_dev(self, unary, image, params, out, unary_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC, stream=None):
+        B = image.shape[0]
+        check(self._L.dsrg_crf_batch_dev(self.h, B, _dptr(unary), unary_layout, _dptr(image), C.byref(params),
+                                         _dptr(out), out_layout, _stream(stream)))
+        return out
+
+    def crf_map_dev(self, unary, image, params, labels_out, unary_layout=LAYOUT_NHWC, stream=None):
+        B = image.shape[0]
+        check(self._L.dsrg_crf_map_batch_dev(self.h, B, _dptr(unary), unary_layout, _dptr(image), C.byref(params),
+                                             _dptr(labels_out), _stream(stream)))
+        return labels_out
+
+    def srg_dev(self, labels, probs, cues, th1, th2, seeds_out, renorm=False, label_map_out=None, stream=None):
+        B = probs.shape[0]
+        check(self._L.dsrg_srg_batch_dev(self.h, B, _dptr(labels), _dptr(probs), _dptr(cues), float(th1), float(th2),
+                                         int(bool(renorm)), _dptr(seeds_out), _dptr(label_map_out), _stream(stream)))
+        return seeds_out
+
+    def dsrg_forward_dev(self, labels, probs, cues, image, params, th1, th2, seeds_out, crf_out=None, stream=None):
+        B = probs.shape[0]
+        check(self._L.dsrg_dsrg_forward_dev(self.h, B, _dptr(labels), _dptr(probs), _dptr(cues), _dptr(image),
+                                            C.byref(params), float(th1), float(th2), _dptr(seeds_out),
+                                            _dptr(crf_out), _stream(stream)))
+        return seeds_out
+
+    def crflayer_forward_dev(self, probs, image, params, log_out, result=None, stream=None):
+        B = probs.shape[0]
+        check(self._L.dsrg_crflayer_forward_dev(self.h, B, _dptr(probs), _dptr(image), C.byref(params),
+                                                _dptr(log_out), _dptr(result), _stream(stream)))
+        return log_out
+
+    def seedloss_forward_dev(self, probs, seeds, terms_out, stream=None):
+        B = probs.shape[0]
+        check(self._L.dsrg_seedloss_forward_dev(self.h, B, _dptr(probs), _dptr(seeds), _dptr(terms_out), _stream(stream)))
+        return terms_out
+
+    def seedloss_backward_dev(self, probs, seeds, grad_out, n_global=None, top_diff=1.0, stream=None):
+        B = probs.shape[0]
+        check(self._L.dsrg_seedloss_backward_dev(self.h, B, int(n_global or B), _dptr(probs), _dptr(seeds),
+                                                 float(top_diff), _dptr(grad_out), _stream(stream)))
+        return grad_out
+
+    # ---- host entry points (numpy; H2D / D2H inside the call) ----
+    def crf_host(self, unary, image, params, out=None, unary_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC):
+        B = image.shape[0]
+        if out is None:
+            shape = (B, self.H, self.W, self.M) if out_layout == LAYOUT_NHWC else (B, self.M, self.H, self.W)
+            out = np.empty(shape, np.float32)
+        check(self._L.dsrg_crf_batch_host(self.h, B, _hptr(unary, np.float32), unary_layout, _hptr(image, np.uint8),
+                                          C.byref(params), _hptr(out, np.float32), out_layout))
+        return out
+
+    def srg_host(self, labels, probs, cues, th1, th2, renorm=False, seeds_out=None, label_map_out=None):
+        B = probs.shape[0]
+        if seeds_out is None:
+            seeds_out = np.empty(probs.shape, np.float32)
+        check(self._L.dsrg_srg_batch_host(self.h, B, _hptr(labels, np.float32), _hptr(probs, np.float32),
+                                          _hptr(cues, np.float32), float(th1), float(th2), int(bool(renorm)),
+                                          _hptr(seeds_out, np.float32), _hptr(label_map_out, np.int32)))
+        return seeds_out
+
+    def dsrg_forward_host(self, labels, probs, cues, image, params, th1, th2, seeds_out=None, crf_out=None):
+        B = probs.shape[0]
+        if seeds_out is None:
+            seeds_out = np.empty(probs.shape, np.float32)
+        check(self._L.dsrg_dsrg_forward_host(self.h, B, _hptr(labels, np.float32), _hptr(probs, np.float32),
+                                             _hptr(cues, np.float32), _hptr(image, np.uint8), C.byref(params),
+                                             float(th1), float(th2), _hptr(seeds_out, np.float32),
+                                             _hptr(crf_out, np.float32)))
+        return seeds_out
+
+    # ---- introspection ----
+    def lattice_sizes(self, B):
+        vs = np.zeros(1, np.int32)
+        vb = np.zeros(B, np.int32)
+        check(self._L.dsrg_engine_lattice_sizes(self.h, B, _hptr(vs, np.int32), _hptr(vb, np.int32)))
+        return int(vs[0]), vb
+
+    def norms(self, B):
+        ns = np.zeros(self.H * self.W, np.float32)
+        nb = np.zeros((B, self.H * self.W), np.float32)
+        check(self._L.dsrg_engine_copy_norm(self.h, 0, B, _hptr(ns, np.float32)))
+        check(self._L.dsrg_engine_copy_norm(self.h, 1, B, _hptr(nb, np.float32)))
+        return ns, nb
+
+
+class DenseCRF(object):
+    """Same surface as the reference's Cython extension type krahenbuhl2013.wrapper.DenseCRF
+    (CRF/krahenbuhl2013/wrapper.pyx:20-60), backed by dsrg_densecrf_* (host pointers)."""
+
+    def __init__(self, W, H, nlabels):
+        self._L = _lib.lib()
+        self.h = self._L.dsrg_densecrf_create(int(W), int(H), int(nlabels))
+        if not self.h:
+            raise DsrgError(_lib.E_CUDA, self._L.dsrg_last_error().decode())
+        self._n = int(W) * int(H)
+        self._m = int(nlabels)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self._L.dsrg_densecrf_destroy(self.h)
+            self.h = None
+
+    def set_unary_energy(self, unary_costs):
+        u = np.ascontiguousarray(unary_costs, np.float32)  # float[:] memoryview in the reference
+        if u.ndim != 1 or u.size != self._n * self._m:
+            raise ValueError("unary_costs must be a flat float32 buffer of npixels*nlabels")
+        check(self._L.dsrg_densecrf_set_unary_energy(self.h, _hptr(u, np.float32)))
+
+    def add_pairwise_energy(self, w1, theta_alpha_1, theta_alpha_2, theta_betta_1, theta_betta_2, theta_betta_3,
+                            w2, theta_gamma_1, theta_gamma_2, im):
+        im = np.ascontiguousarray(im, np.uint8)  # unsigned char[:] in the reference
+        if im.ndim != 1 or im.size != self._n * 3:
+            raise ValueError("im must be a flat uint8 buffer of npixels*3")
+        check(self._L.dsrg_densecrf_add_pairwise_energy(self.h, w1, theta_alpha_1, theta_alpha_2, theta_betta_1,
+                                                        theta_betta_2, theta_betta_3, w2, theta_gamma_1,
+                                                        theta_gamma_2, _hptr(im, np.uint8)))
+
+    def map(self, n_iters=10):
+        labels = np.empty(self._n, dtype=np.int32)
+        check(self._L.dsrg_densecrf_map(self.h, int(n_iters), _hptr(labels, np.int32)))
+        return labels
+
+    def inference(self, n_iters=10):
+        probs = np.empty(self._n * self._m, dtype=np.float32)
+        check(self._L.dsrg_densecrf_inference(self.h, int(n_iters), _hptr(probs, np.float32)))
+        return probs

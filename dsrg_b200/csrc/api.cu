@@ -1,0 +1,642 @@
+// C ABI of the B200-native DSRG hot path (see include/dsrg_b200.h for the contract and the
+// reference interfaces each entry point replaces).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace dsrg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int device_alloc(Engine *e, void **p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t err = cudaMalloc(p, bytes);
+    if (err != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+        *p = nullptr;
+        return DSRG_E_NOMEM;
+    }
+    e->bytes += bytes;
+    return DSRG_OK;
+}
+
+// elevation scale factors exactly as the reference computes them (permutohedral.cpp:179-182):
+// float inv_std_dev = sqrt(2/3)*(d+1); scale[i] = float(1.0/sqrt((i+2)*(i+1)) * inv_std_dev)
+static void lattice_scales(Lattice &L) {
+    const float inv_std_dev = (float)(sqrt(2.0 / 3.0) * (L.d + 1));
+    for (int i = 0; i < L.d; i++)
+        L.scale[i] = (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * (double)inv_std_dev);
+}
+
+// conservative host-side bound on |lattice key| so that range problems surface as an error code
+// before anything is launched (the kernels keep a device-side flag as a second line of defence)
+static bool key_range_ok(const Lattice &L, int W, int H) {
+    double fmax[5] = {(W - 1) / (double)L.sigma[0], (H - 1) / (double)L.sigma[1], 0, 0, 0};
+    for (int i = 2; i < L.d; i++) fmax[i] = 255.0 / (double)L.sigma[i];
+    double sum = 0, big = 0;
+    for (int i = 0; i < L.d; i++) {
+        double cf = fabs(fmax[i]) * L.scale[i];
+        sum += cf;
+        if ((i + 1) * cf > big) big = (i + 1) * cf;
+    }
+    const double bound = sum + big + 3.0 * (L.d + 1) + 2;
+    const int bits = (L.d == 2) ? 16 : 12;
+    return bound < (double)((1 << (bits - 1)) - 1) && isfinite(bound);
+}
+
+static int lattice_alloc(Engine *e, Lattice &L, int d, int shared) {
+    L.d = d;
+    L.shared = shared;
+    L.nimg = shared ? 1 : e->maxB;
+    L.N = e->N;
+    L.P = (4 - (e->N % 4)) % 4;
+    L.capv = (L.N + L.P) * (d + 1);
+    L.cap = 2 * L.capv;
+    L.rows_cap = (long long)e->maxB * (L.capv + 1);
+    L.nbr_stride = shared ? (long long)L.capv + 1 : L.rows_cap;
+    const size_t n = (size_t)L.nimg;
+    int rc = 0;
+    rc |= dalloc(e, &L.off, n * (d + 1) * L.N);
+    rc |= dalloc(e, &L.bary, n * (d + 1) * L.N);
+    rc |= dalloc(e, &L.norm, n * L.N);
+    rc |= dalloc(e, &L.hkeys, n * L.cap);
+    rc |= dalloc(e, &L.hval, n * L.cap);
+    rc |= dalloc(e, &L.vslot, n * L.capv);
+    rc |= dalloc(e, &L.vcount, n);
+    rc |= dalloc(e, &L.rowbase, (size_t)e->maxB + 1);
+    rc |= dalloc(e, &L.nbr, (size_t)(d + 1) * L.nbr_stride);
+    if (rc) return DSRG_E_NOMEM;
+    if (cudaMemset(L.hkeys, 0xFF, sizeof(uint64_t) * n * L.cap) != cudaSuccess) return DSRG_E_CUDA;
+    return DSRG_OK;
+}
+
+static void lattice_free(Lattice &L) {
+    cudaFree(L.off);
+    cudaFree(L.bary);
+    cudaFree(L.norm);
+    cudaFree(L.hkeys);
+    cudaFree(L.hval);
+    cudaFree(L.vslot);
+    cudaFree(L.vcount);
+    cudaFree(L.rowbase);
+    cudaFree(L.nbr);
+}
+
+static int check_device_flag(Engine *e, cudaStream_t s) {
+    int flag = 0;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(&flag, e->dev_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    DSRG_CUDA_TRY(cudaStreamSynchronize(s));
+    if (flag != 0) {
+        cudaMemsetAsync(e->dev_err, 0, sizeof(int), s);
+        set_error("lattice coordinates exceed the packed-key range (sigma too small for this image size)");
+        return flag;
+    }
+    return DSRG_OK;
+}
+
+// (re)build lattices for this call: spatial only when its sigmas changed, bilateral always
+static int prepare_lattices(Engine *e, int B, const uint8_t *image, const dsrg_crf_params &p,
+                            cudaStream_t s) {
+    if (!(p.theta_gamma_x > 0 && p.theta_gamma_y > 0 && p.theta_alpha_x > 0 && p.theta_alpha_y > 0 &&
+          p.theta_beta_r > 0 && p.theta_beta_g > 0 && p.theta_beta_b > 0) || p.n_iters < 0) {
+        set_error("CRF parameters must be positive");
+        return DSRG_E_INVALID;
+    }
+    if (!e->sp_valid || e->sp.sigma[0] != p.theta_gamma_x || e->sp.sigma[1] != p.theta_gamma_y) {
+        e->sp.sigma[0] = p.theta_gamma_x;
+        e->sp.sigma[1] = p.theta_gamma_y;
+        if (!key_range_ok(e->sp, e->W, e->H)) {
+            set_error("spatial sigma (%g,%g) too small for %dx%d: lattice keys exceed 16 bits",
+                      p.theta_gamma_x, p.theta_gamma_y, e->W, e->H);
+            return DSRG_E_KEYRANGE;
+        }
+        int rc = lattice_build(e, e->sp, B, nullptr, s);
+        if (rc) return rc;
+        e->sp_valid = true;
+    }
+    e->bi.sigma[0] = p.theta_alpha_x;
+    e->bi.sigma[1] = p.theta_alpha_y;
+    e->bi.sigma[2] = p.theta_beta_r;
+    e->bi.sigma[3] = p.theta_beta_g;
+    e->bi.sigma[4] = p.theta_beta_b;
+    if (!key_range_ok(e->bi, e->W, e->H)) {
+        set_error("bilateral sigmas too small for %dx%d: lattice keys exceed the 12-bit packed range",
+                  e->W, e->H);
+        return DSRG_E_KEYRANGE;
+    }
+    return lattice_build(e, e->bi, B, image, s);
+}
+
+static int check_batch(Engine *e, int B) {
+    if (!e) {
+        set_error("engine is NULL");
+        return DSRG_E_INVALID;
+    }
+    if (B < 1 || B > e->maxB) {
+        set_error("batch %d outside [1, %d]", B, e->maxB);
+        return DSRG_E_INVALID;
+    }
+    DSRG_CUDA_TRY(cudaSetDevice(e->device));
+    return DSRG_OK;
+}
+
+static int crf_core(Engine *e, int B, const float *unary, int layout, bool clamp, float *unary_rw,
+                    const uint8_t *image, const dsrg_crf_params *p, cudaStream_t s) {
+    if (!unary || !image || !p) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    if (layout != DSRG_LAYOUT_NHWC && layout != DSRG_LAYOUT_NCHW) {
+        set_error("bad layout %d", layout);
+        return DSRG_E_INVALID;
+    }
+    int rc = prepare_lattices(e, B, image, *p, s);
+    if (rc) return rc;
+    return meanfield_run(e, B, unary, layout, clamp, unary_rw, *p, s);
+}
+
+static int ensure_staging(Engine *e) {
+    if (e->st_unary) return DSRG_OK;
+    const size_t n = (size_t)e->maxB * e->M * e->N;
+    int rc = 0;
+    rc |= dalloc(e, &e->st_unary, n);
+    rc |= dalloc(e, &e->st_out, n);
+    rc |= dalloc(e, &e->st_cues, n);
+    rc |= dalloc(e, &e->st_labels, (size_t)e->maxB * e->M);
+    rc |= dalloc(e, &e->st_image, (size_t)e->maxB * e->N * 3);
+    rc |= dalloc(e, &e->st_lmap, (size_t)e->maxB * e->N);
+    return rc ? DSRG_E_NOMEM : DSRG_OK;
+}
+
+}  // namespace dsrg
+
+using namespace dsrg;
+
+extern "C" {
+
+int dsrg_version(void) { return 100; }
+
+const char *dsrg_last_error(void) { return g_err; }
+
+int dsrg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void *dsrg_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+        set_error("cudaHostAlloc(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void dsrg_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+void dsrg_crf_params_default(dsrg_crf_params *p, float scale_factor, float color_factor, int maxiter) {
+    // CRF/krahenbuhl2013/CRF.py:31-32
+    p->w1 = 10.0f;
+    p->theta_alpha_x = p->theta_alpha_y = (float)(80.0 / (double)scale_factor);
+    p->theta_beta_r = p->theta_beta_g = p->theta_beta_b = color_factor;
+    p->w2 = 3.0f;
+    p->theta_gamma_x = p->theta_gamma_y = (float)(3.0 / (double)scale_factor);
+    p->n_iters = maxiter;
+}
+
+dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) {
+    if (max_batch < 1 || H < 1 || W < 1 || M < 1 || M > DSRG_MAX_LABELS ||
+        (long long)H * W > (1ll << 24)) {
+        set_error("bad engine shape (max_batch=%d H=%d W=%d M=%d; M <= %d)", max_batch, H, W, M,
+                  DSRG_MAX_LABELS);
+        return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        set_error("no usable CUDA device %d (visible devices: %d): this library has no CPU fallback",
+                  device, ndev);
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        set_error("cannot select device %d", device);
+        return nullptr;
+    }
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major,
+                  prop.minor);
+        return nullptr;
+    }
+    Engine *e = new (std::nothrow) Engine();
+    if (!e) return nullptr;
+    e->device = device;
+    e->maxB = max_batch;
+    e->H = H;
+    e->W = W;
+    e->M = M;
+    e->MP = (M + 3) / 4 * 4;
+    e->N = H * W;
+    e->sm_count = prop.multiProcessorCount;
+    int rc = 0;
+    rc |= lattice_alloc(e, e->sp, 2, 1);
+    rc |= lattice_alloc(e, e->bi, 5, 0);
+    lattice_scales(e->sp);
+    lattice_scales(e->bi);
+    const size_t n = (size_t)max_batch * M * e->N;
+    rc |= dalloc(e, &e->U, n);
+    rc |= dalloc(e, &e->Q0, n);
+    rc |= dalloc(e, &e->Q1, n);
+    rc |= dalloc(e, &e->spA, (size_t)e->sp.rows_cap * e->MP);
+    rc |= dalloc(e, &e->spB, (size_t)e->sp.rows_cap * e->MP);
+    rc |= dalloc(e, &e->biA, (size_t)e->bi.rows_cap * e->MP);
+    rc |= dalloc(e, &e->biB, (size_t)e->bi.rows_cap * e->MP);
+    rc |= dalloc(e, &e->nvA, (size_t)e->bi.rows_cap);
+    rc |= dalloc(e, &e->nvB, (size_t)e->bi.rows_cap);
+    const size_t bn = (size_t)max_batch * e->N;
+    rc |= dalloc(e, &e->lmap, bn);
+    rc |= dalloc(e, &e->lflag, bn);
+    rc |= dalloc(e, &e->parent, bn);
+    rc |= dalloc(e, &e->hc, bn);
+    rc |= dalloc(e, &e->loss_acc, (size_t)max_batch * 4);
+    rc |= dalloc(e, &e->dev_err, 1);
+    if (!rc && cudaMemset(e->dev_err, 0, sizeof(int)) != cudaSuccess) rc = DSRG_E_CUDA;
+    if (!rc && cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
+    if (rc) {
+        dsrg_engine_destroy((dsrg_engine *)e);
+        return nullptr;
+    }
+    e->Qcur = e->Q0;
+    return (dsrg_engine *)e;
+}
+
+void dsrg_engine_destroy(dsrg_engine *h) {
+    Engine *e = (Engine *)h;
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    lattice_free(e->sp);
+    lattice_free(e->bi);
+    void *ptrs[] = {e->U, e->Q0, e->Q1, e->spA, e->spB, e->biA, e->biB, e->nvA, e->nvB, e->lmap,
+                    e->lflag, e->parent, e->hc, e->loss_acc, e->dev_err, e->st_unary, e->st_out,
+                    e->st_cues, e->st_labels, e->st_image, e->st_lmap};
+    for (void *p : ptrs) cudaFree(p);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+size_t dsrg_engine_device_bytes(const dsrg_engine *h) { return h ? ((const Engine *)h)->bytes : 0; }
+
+long long dsrg_engine_take_launch_count(dsrg_engine *h) {
+    Engine *e = (Engine *)h;
+    if (!e) return 0;
+    long long n = e->launches;
+    e->launches = 0;
+    return n;
+}
+
+int dsrg_crf_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layout,
+                       const uint8_t *image, const dsrg_crf_params *params, float *out,
+                       int out_layout, void *stream) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!out || (out_layout != DSRG_LAYOUT_NHWC && out_layout != DSRG_LAYOUT_NCHW)) {
+        set_error("bad output argument");
+        return DSRG_E_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = crf_core(e, B, unary, unary_layout, false, nullptr, image, params, s);
+    if (rc) return rc;
+    return meanfield_export(e, B, out, out_layout, s);
+}
+
+int dsrg_crf_map_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layout,
+                           const uint8_t *image, const dsrg_crf_params *params, int32_t *labels_out,
+                           void *stream) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!labels_out) {
+        set_error("labels_out is NULL");
+        return DSRG_E_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = crf_core(e, B, unary, unary_layout, false, nullptr, image, params, s);
+    if (rc) return rc;
+    return meanfield_export_map(e, B, labels_out, s);
+}
+
+int dsrg_crf_batch_host(dsrg_engine *h, int B, const float *unary, int unary_layout,
+                        const uint8_t *image, const dsrg_crf_params *params, float *out,
+                        int out_layout) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!unary || !image || !out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    if ((rc = ensure_staging(e))) return rc;
+    cudaStream_t s = e->own_stream;
+    const size_t n = (size_t)B * e->M * e->N;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, unary, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image, image, (size_t)B * e->N * 3, cudaMemcpyHostToDevice, s));
+    rc = dsrg_crf_batch_dev(h, B, e->st_unary, unary_layout, e->st_image, params, e->st_out, out_layout, s);
+    if (rc) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(out, e->st_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    return check_device_flag(e, s);
+}
+
+int dsrg_srg_batch_dev(dsrg_engine *h, int B, const float *labels, const float *probs,
+                       const float *cues, double th1, double th2, int renorm, float *seeds_out,
+                       int32_t *label_map_out, void *stream) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!labels || !probs || !cues || !seeds_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    if (e->M > 255) {
+        set_error("SRG supports at most 255 classes");
+        return DSRG_E_INVALID;
+    }
+    return srg_run(e, B, labels, probs, cues, th1, th2, renorm, seeds_out, label_map_out,
+                   (cudaStream_t)stream);
+}
+
+int dsrg_srg_batch_host(dsrg_engine *h, int B, const float *labels, const float *probs,
+                        const float *cues, double th1, double th2, int renorm, float *seeds_out,
+                        int32_t *label_map_out) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!labels || !probs || !cues || !seeds_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    if ((rc = ensure_staging(e))) return rc;
+    cudaStream_t s = e->own_stream;
+    const size_t n = (size_t)B * e->M * e->N;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_labels, labels, (size_t)B * e->M * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, cues, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = dsrg_srg_batch_dev(h, B, e->st_labels, e->st_unary, e->st_cues, th1, th2, renorm, e->st_out,
+                            label_map_out ? e->st_lmap : nullptr, s);
+    if (rc) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(seeds_out, e->st_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (label_map_out)
+        DSRG_CUDA_TRY(cudaMemcpyAsync(label_map_out, e->st_lmap, (size_t)B * e->N * sizeof(int32_t),
+                                      cudaMemcpyDeviceToHost, s));
+    DSRG_CUDA_TRY(cudaStreamSynchronize(s));
+    return DSRG_OK;
+}
+
+int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *probs,
+                          const float *cues, const uint8_t *image, const dsrg_crf_params *params,
+                          double th1, double th2, float *seeds_out, float *crf_out, void *stream) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!labels || !probs || !cues || !seeds_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    // refinement (pylayers.py:310-331): in-place clamp, unary = probs (NCHW), CRF
+    rc = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
+    if (rc) return rc;
+    if (crf_out && (rc = meanfield_export(e, B, crf_out, DSRG_LAYOUT_NCHW, s))) return rc;
+    // SRG on the raw marginals with the float64 clamp + renormalisation fused in (renorm = 1)
+    return srg_run(e, B, labels, e->Qcur, cues, th1, th2, 1, seeds_out, nullptr, s);
+}
+
+int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels, float *probs,
+                           const float *cues, const uint8_t *image, const dsrg_crf_params *params,
+                           double th1, double th2, float *seeds_out, float *crf_out) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!labels || !probs || !cues || !image || !seeds_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    if ((rc = ensure_staging(e))) return rc;
+    cudaStream_t s = e->own_stream;
+    const size_t n = (size_t)B * e->M * e->N;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_labels, labels, (size_t)B * e->M * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, cues, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image, image, (size_t)B * e->N * 3, cudaMemcpyHostToDevice, s));
+    // seeds land in st_out; the optional raw marginals are exported into st_cues afterwards
+    // (the SRG has consumed the cues by then; same stream, so ordered)
+    rc = dsrg_dsrg_forward_dev(h, B, e->st_labels, e->st_unary, e->st_cues, e->st_image, params, th1,
+                               th2, e->st_out, nullptr, s);
+    if (rc) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(seeds_out, e->st_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    // the reference mutates the probs blob in place (pylayers.py:312): hand the clamped values back
+    DSRG_CUDA_TRY(cudaMemcpyAsync(probs, e->st_unary, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (crf_out) {
+        if ((rc = meanfield_export(e, B, e->st_cues, DSRG_LAYOUT_NCHW, s))) return rc;
+        DSRG_CUDA_TRY(cudaMemcpyAsync(crf_out, e->st_cues, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    return check_device_flag(e, s);
+}
+
+int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t *image,
+                              const dsrg_crf_params *params, float *log_out, float *result,
+                              void *stream) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!probs || !log_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
+    if (rc) return rc;
+    return meanfield_export_renorm(e, B, result, log_out, s);
+}
+
+int dsrg_seedloss_forward_dev(dsrg_engine *h, int B, const float *probs, const float *seeds,
+                              float *terms_out, void *stream) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!probs || !seeds || !terms_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    return seedloss_forward(e, B, probs, seeds, terms_out, (cudaStream_t)stream);
+}
+
+int dsrg_seedloss_backward_dev(dsrg_engine *h, int B, int n_global, const float *probs,
+                               const float *seeds, float top_diff, float *grad, void *stream) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!probs || !seeds || !grad || n_global < 1) {
+        set_error("bad argument");
+        return DSRG_E_INVALID;
+    }
+    return seedloss_backward(e, B, n_global, probs, seeds, top_diff, grad, (cudaStream_t)stream);
+}
+
+int dsrg_engine_lattice_sizes(dsrg_engine *h, int B, int *v_spatial, int *v_bilateral) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    DSRG_CUDA_TRY(cudaDeviceSynchronize());
+    if (v_spatial) DSRG_CUDA_TRY(cudaMemcpy(v_spatial, e->sp.vcount, sizeof(int), cudaMemcpyDeviceToHost));
+    if (v_bilateral)
+        DSRG_CUDA_TRY(cudaMemcpy(v_bilateral, e->bi.vcount, sizeof(int) * B, cudaMemcpyDeviceToHost));
+    return DSRG_OK;
+}
+
+int dsrg_engine_copy_norm(dsrg_engine *h, int which, int B, float *norm_out) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    DSRG_CUDA_TRY(cudaDeviceSynchronize());
+    if (which == 0)
+        DSRG_CUDA_TRY(cudaMemcpy(norm_out, e->sp.norm, sizeof(float) * e->N, cudaMemcpyDeviceToHost));
+    else
+        DSRG_CUDA_TRY(cudaMemcpy(norm_out, e->bi.norm, sizeof(float) * (size_t)B * e->N, cudaMemcpyDeviceToHost));
+    return DSRG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DenseCRFWrapper-shaped object API (CRF/include/densecrf_wrapper.h:3-28)
+// ------------------------------------------------------------------------------------------------
+struct dsrg_densecrf {
+    int W, H, M;
+    dsrg_engine *engine;
+    std::vector<float> unary;          // negated energies == the `unary` of CRF()
+    std::vector<unsigned char> image;
+    dsrg_crf_params params;
+    bool has_unary, has_pairwise;
+};
+
+dsrg_densecrf *dsrg_densecrf_create(int W, int H, int nlabels) {
+    dsrg_engine *eng = dsrg_engine_create(0, 1, H, W, nlabels);
+    if (!eng) return nullptr;
+    dsrg_densecrf *c = new (std::nothrow) dsrg_densecrf();
+    if (!c) {
+        dsrg_engine_destroy(eng);
+        return nullptr;
+    }
+    c->W = W;
+    c->H = H;
+    c->M = nlabels;
+    c->engine = eng;
+    c->has_unary = c->has_pairwise = false;
+    return c;
+}
+
+void dsrg_densecrf_destroy(dsrg_densecrf *c) {
+    if (!c) return;
+    dsrg_engine_destroy(c->engine);
+    delete c;
+}
+
+int dsrg_densecrf_npixels(const dsrg_densecrf *c) { return c ? c->W * c->H : 0; }
+int dsrg_densecrf_nlabels(const dsrg_densecrf *c) { return c ? c->M : 0; }
+
+int dsrg_densecrf_set_unary_energy(dsrg_densecrf *c, const float *unary_costs) {
+    if (!c || !unary_costs) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    const size_t n = (size_t)c->W * c->H * c->M;
+    c->unary.resize(n);
+    for (size_t i = 0; i < n; i++) c->unary[i] = -unary_costs[i];  // Q0 = softmax(-energy), densecrf.cpp:120
+    c->has_unary = true;
+    return DSRG_OK;
+}
+
+int dsrg_densecrf_add_pairwise_energy(dsrg_densecrf *c, float w1, float theta_alpha_1,
+                                      float theta_alpha_2, float theta_betta_1, float theta_betta_2,
+                                      float theta_betta_3, float w2, float theta_gamma_1,
+                                      float theta_gamma_2, const unsigned char *im) {
+    if (!c || !im) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    c->params.w1 = w1;
+    c->params.theta_alpha_x = theta_alpha_1;
+    c->params.theta_alpha_y = theta_alpha_2;
+    c->params.theta_beta_r = theta_betta_1;
+    c->params.theta_beta_g = theta_betta_2;
+    c->params.theta_beta_b = theta_betta_3;
+    c->params.w2 = w2;
+    c->params.theta_gamma_x = theta_gamma_1;
+    c->params.theta_gamma_y = theta_gamma_2;
+    c->image.assign(im, im + (size_t)c->W * c->H * 3);
+    c->has_pairwise = true;
+    return DSRG_OK;
+}
+
+static int densecrf_run(dsrg_densecrf *c, int n_iters) {
+    if (!c) {
+        set_error("NULL object");
+        return DSRG_E_INVALID;
+    }
+    if (!c->has_pairwise) {
+        set_error("add_pairwise_energy must be called before inference/map");
+        return DSRG_E_STATE;
+    }
+    Engine *e = (Engine *)c->engine;
+    int rc = ensure_staging(e);
+    if (rc) return rc;
+    if (!c->has_unary) c->unary.assign((size_t)c->W * c->H * c->M, 0.0f);  // unary.fill(0), densecrf.cpp:117
+    c->params.n_iters = n_iters;
+    cudaStream_t s = e->own_stream;
+    DSRG_CUDA_TRY(cudaSetDevice(e->device));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, c->unary.data(), c->unary.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image, c->image.data(), c->image.size(), cudaMemcpyHostToDevice, s));
+    return crf_core(e, 1, e->st_unary, DSRG_LAYOUT_NHWC, false, nullptr, e->st_image, &c->params, s);
+}
+
+int dsrg_densecrf_inference(dsrg_densecrf *c, int n_iters, float *probs_out) {
+    int rc = densecrf_run(c, n_iters);
+    if (rc) return rc;
+    Engine *e = (Engine *)c->engine;
+    cudaStream_t s = e->own_stream;
+    if ((rc = meanfield_export(e, 1, e->st_out, DSRG_LAYOUT_NHWC, s))) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(probs_out, e->st_out, c->unary.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    return check_device_flag(e, s);
+}
+
+int dsrg_densecrf_map(dsrg_densecrf *c, int n_iters, int *labels) {
+    int rc = densecrf_run(c, n_iters);
+    if (rc) return rc;
+    Engine *e = (Engine *)c->engine;
+    cudaStream_t s = e->own_stream;
+    if ((rc = meanfield_export_map(e, 1, e->st_lmap, s))) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(labels, e->st_lmap, (size_t)c->W * c->H * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return check_device_flag(e, s);
+}
+
+}  // extern "C"

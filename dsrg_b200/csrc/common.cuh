@@ -1,0 +1,115 @@
+// Shared declarations of the B200-native DSRG hot path (internal; the public surface is
+// include/dsrg_b200.h).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dsrg_b200.h"
+
+namespace dsrg {
+
+constexpr int kThreads = 256;
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr float kMinProb = 0.0001f;  // pylayers/pylayers/pylayers.py:20
+
+void set_error(const char *fmt, ...);
+
+#define DSRG_CUDA_TRY(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            dsrg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                            __FILE__, __LINE__);                                         \
+            return DSRG_E_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// One permutohedral lattice family (spatial d=2 shared by the batch, or bilateral d=5 per image).
+// Value rows: image b owns rows [rowbase[b], rowbase[b+1]); the first one is an all-zero row
+// that stands for "missing neighbour" (the reference shifts ids by +1 for the same purpose,
+// CRF/src/permutohedral.cpp:478-479, :534).
+struct Lattice {
+    int d = 0;
+    int shared = 0;         // 1: one structure (image 0) reused by every image of the batch
+    int nimg = 0;           // structures held (1 if shared, else max_batch)
+    int N = 0;              // pixels
+    int P = 0;              // phantom lanes (permutohedral.cpp:196: tail of the last 4-block)
+    int cap = 0;            // hash slots per structure
+    int capv = 0;           // max vertices per structure = (N+P)*(d+1)
+    long long rows_cap = 0; // rows in the value buffers (all images)
+    int32_t *off = nullptr;     // [nimg][d+1][N] local row (1-based; 0 = zero row)
+    float *bary = nullptr;      // [nimg][d+1][N]
+    float *norm = nullptr;      // [nimg][N]
+    uint64_t *hkeys = nullptr;  // [nimg][cap]
+    int32_t *hval = nullptr;    // [nimg][cap] local vertex id of the slot
+    int32_t *vslot = nullptr;   // [nimg][capv] slot of local vertex id
+    int32_t *vcount = nullptr;  // [nimg]
+    int32_t *rowbase = nullptr; // [max_batch+1]
+    int2 *nbr = nullptr;        // [d+1][rows] (n1,n2): global rows (per-image) or local rows (shared)
+    long long nbr_stride = 0;   // rows per axis in nbr
+    float scale[5] = {0, 0, 0, 0, 0};  // elevation scale factors (permutohedral.cpp:179-182)
+    float sigma[5] = {0, 0, 0, 0, 0};  // feature sigmas: x, y[, c0, c1, c2]
+};
+
+struct Engine;
+
+// ---- lattice.cu ----
+int lattice_build(Engine *e, Lattice &L, int B, const uint8_t *image_dev, cudaStream_t s);
+// ---- meanfield.cu ----
+int meanfield_run(Engine *e, int B, const float *unary, int unary_layout, bool clamp_inplace,
+                  float *unary_rw, const dsrg_crf_params &p, cudaStream_t s);
+int meanfield_export(Engine *e, int B, float *out, int layout, cudaStream_t s);
+int meanfield_export_map(Engine *e, int B, int32_t *labels, cudaStream_t s);
+int meanfield_export_renorm(Engine *e, int B, float *result_out, float *log_out, cudaStream_t s);
+// ---- srg.cu ----
+int srg_run(Engine *e, int B, const float *labels, const float *probs, const float *cues,
+            double th1, double th2, int renorm, float *seeds_out, int32_t *label_map_out,
+            cudaStream_t s);
+// ---- loss.cu ----
+int seedloss_forward(Engine *e, int B, const float *probs, const float *seeds, float *terms_out,
+                     cudaStream_t s);
+int seedloss_backward(Engine *e, int B, int n_global, const float *probs, const float *seeds,
+                      float top_diff, float *grad, cudaStream_t s);
+
+struct Engine {
+    int device = 0;
+    int maxB = 0, H = 0, W = 0, M = 0, MP = 0, N = 0;
+    int sm_count = 148;
+    size_t bytes = 0;
+    long long launches = 0;
+
+    Lattice sp, bi;
+    bool sp_valid = false;
+
+    // mean-field state, planar [B][M][N]
+    float *U = nullptr, *Q0 = nullptr, *Q1 = nullptr;
+    float *Qcur = nullptr;  // where the current marginals live (Q0 or Q1)
+    // lattice value buffers [rows][MP]
+    float *spA = nullptr, *spB = nullptr, *biA = nullptr, *biB = nullptr;
+    // 1-channel buffers for the normalisation pass
+    float *nvA = nullptr, *nvB = nullptr;
+    // SRG state
+    uint8_t *lmap = nullptr;   // [B][N] label map value (0 = none, c+1)
+    uint8_t *lflag = nullptr;  // [B][N] bit0 own-seed, bit1 excluded
+    int32_t *parent = nullptr; // [B][N] union-find forest
+    uint8_t *hc = nullptr;     // [B][N] high-confidence flag per root
+    // loss scratch
+    double *loss_acc = nullptr;  // [B][4]
+    // staging for the *_host entry points
+    float *st_unary = nullptr, *st_out = nullptr, *st_cues = nullptr, *st_labels = nullptr;
+    uint8_t *st_image = nullptr;
+    int32_t *st_lmap = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int *dev_err = nullptr;  // device-side error flag
+};
+
+int device_alloc(Engine *e, void **p, size_t bytes);
+template <typename T>
+inline int dalloc(Engine *e, T **p, size_t count) {
+    return device_alloc(e, (void **)p, count * sizeof(T));
+}
+
+}  // namespace dsrg

@@ -1,0 +1,195 @@
+// Seeded region growing for a whole batch (sm_100a).
+//
+// Replaces generate_seed_step (pylayers/pylayers/pylayers.py:237-275) and the pure-Python
+// two-pass labeller it calls per class (pylayers/pylayers/CC_labeling_8.py:103-282).
+//
+// The reference runs one binary 8-connectivity labelling per present class; the class masks
+// label_map == c+1 are disjoint, so ONE equal-label 8-connectivity union-find over the
+// multi-valued label map gives the same components.  Everything is integer /
+// comparison work, hence bit-exact against the reference:
+//   K1 label map   : thresholds compared in float64 exactly like the reference's data
+//   K2 merge       : per-pixel union with the W / NW / N / NE neighbour of equal label; horizontal
+//                    runs are pre-linked with a warp ballot (neighbour voting) so that only run
+//                    heads and vertical links touch the global forest
+//   K3 flag        : components containing an own-class seed become "high confidence"
+//   K4 emit        : seeds_out = cues OR (grown AND NOT excluded)
+#include "common.cuh"
+
+namespace dsrg {
+
+__device__ __forceinline__ int uf_find(const int32_t *parent, int x) {
+    const volatile int32_t *vp = parent;  // other threads hook roots concurrently
+    int p = vp[x];
+    while (p != x) {
+        x = p;
+        p = vp[x];
+    }
+    return x;
+}
+
+// lock-free union by minimum index (label equivalence), safe under concurrent unions
+__device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) {
+            int t = a;
+            a = b;
+            b = t;
+        }
+        int old = atomicMin(parent + b, a);  // hook the larger root under the smaller
+        if (old == b) return;
+        b = old;  // somebody re-hooked b meanwhile: retry from there
+    }
+}
+
+// K1 --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_srg_label(const float *labels, const float *probs, const float *cues, double th1, double th2,
+            int renorm, uint8_t *lmap, uint8_t *lflag, int32_t *parent, uint8_t *hc,
+            int32_t *label_map_out, int M, int N, int W) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < N;
+    int L = 0;
+    if (in) {
+        const float *lab = labels + (size_t)b * M;
+        const float *pb = probs + (size_t)b * M * N + i;
+        const float *cb = cues + (size_t)b * M * N + i;
+        // optional post-CRF renormalisation in float64 (pylayers.py:328-330)
+        double s = 1.0;
+        if (renorm) {
+            s = 0.0;
+            for (int c = 0; c < M; c++) {
+                double v = (double)pb[(size_t)c * N];
+                if (v < 0.0001) v = 0.0001;
+                s += v;
+            }
+        }
+        // arg-max / max over the PRESENT classes, first index wins ties (pylayers.py:240-243)
+        int cstar = -1;
+        double best = 0.0;
+        float nseed = 0.0f;   // np.sum(seed_c[:, x, y]) (pylayers.py:268)
+        float cue_at_L = 0.0f;
+        for (int c = 0; c < M; c++) {
+            const float cu = cb[(size_t)c * N];
+            nseed += cu;
+            if (cu > 0.0f) {  // seeds: the highest class index wins (pylayers.py:248-250)
+                L = c + 1;
+                cue_at_L = cu;
+            }
+            if (lab[c] == 1.0f) {
+                double v = (double)pb[(size_t)c * N];
+                if (renorm) {
+                    if (v < 0.0001) v = 0.0001;
+                    v = v / s;
+                }
+                if (cstar < 0 || v > best) {
+                    best = v;
+                    cstar = c;
+                }
+            }
+        }
+        // thresholds (pylayers.py:251-257): strict > in float64; overwrite the seed label
+        if (cstar >= 0 && best > th2 && (cstar != 0 || best > th1)) {
+            L = cstar + 1;
+            cue_at_L = cb[(size_t)cstar * N];
+        }
+        uint8_t fl = 0;
+        if (L > 0) {
+            const bool present = lab[L - 1] == 1.0f;
+            const bool own = cue_at_L == 1.0f;               // seed_c[c,x,y] == 1 (pylayers.py:266)
+            if (present && own) fl |= 1;
+            if (!own && nseed == 1.0f) fl |= 2;              // excluded (pylayers.py:268-269)
+        }
+        lmap[(size_t)b * N + i] = (uint8_t)L;
+        lflag[(size_t)b * N + i] = fl;
+        hc[(size_t)b * N + i] = 0;
+        if (label_map_out) label_map_out[(size_t)b * N + i] = L;
+    }
+    // horizontal runs via warp ballot: a pixel links to the head of its run inside the warp's
+    // 32-pixel window, so W-links never go through atomics
+    const unsigned lane = threadIdx.x & 31;
+    const int x = in ? i % W : 0;
+    const int left = __shfl_up_sync(0xffffffffu, L, 1);
+    const bool joins_left = in && lane > 0 && x > 0 && L > 0 && left == L;
+    const unsigned brk = ~__ballot_sync(0xffffffffu, joins_left);  // bit set = run head
+    if (in) {
+        const unsigned below = brk & (0xffffffffu >> (31 - lane));  // heads at lanes <= mine
+        const int head_lane = 31 - __clz(below);
+        parent[(size_t)b * N + i] = i - ((int)lane - head_lane);
+    }
+}
+
+// K2 --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_srg_merge(const uint8_t *lmap, int32_t *parent, int N, int W) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint8_t *lm = lmap + (size_t)b * N;
+    int32_t *par = parent + (size_t)b * N;
+    const int L = lm[i];
+    if (L == 0) return;
+    const int x = i % W;
+    // W link across a warp-window boundary (inside the window the ballot already linked it)
+    if (x > 0 && (threadIdx.x & 31) == 0 && lm[i - 1] == L) uf_union(par, i, i - 1);
+    if (i >= W) {
+        const int n = i - W;
+        if (lm[n] == L) {
+            uf_union(par, i, n);  // N covers NW and NE through the row above
+        } else {
+            if (x > 0 && lm[n - 1] == L) uf_union(par, i, n - 1);
+            if (x < W - 1 && lm[n + 1] == L) uf_union(par, i, n + 1);
+        }
+    }
+}
+
+// K3 --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_srg_flag(const uint8_t *lflag, int32_t *parent, uint8_t *hc, int N) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int32_t *par = parent + (size_t)b * N;
+    const int root = uf_find(par, i);
+    par[i] = root;  // path compression for K4 (roots never change any more)
+    if (lflag[(size_t)b * N + i] & 1) hc[(size_t)b * N + root] = 1;
+}
+
+// K4 --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_srg_emit(const float *cues, const uint8_t *lmap, const uint8_t *lflag, const int32_t *parent,
+           const uint8_t *hc, float *seeds_out, int M, int N) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const size_t p = (size_t)b * N + i;
+    const int L = lmap[p];
+    int grow_c = -1;
+    if (L > 0 && !(lflag[p] & 2)) {
+        const int root = parent[p];  // fully compressed by K3
+        if (hc[(size_t)b * N + root]) grow_c = L - 1;
+    }
+    const float *cb = cues + (size_t)b * M * N + i;
+    float *ob = seeds_out + (size_t)b * M * N + i;
+    for (int c = 0; c < M; c++) ob[(size_t)c * N] = (c == grow_c) ? 1.0f : cb[(size_t)c * N];
+}
+
+int srg_run(Engine *e, int B, const float *labels, const float *probs, const float *cues,
+            double th1, double th2, int renorm, float *seeds_out, int32_t *label_map_out,
+            cudaStream_t s) {
+    const int N = e->N, M = e->M;
+    dim3 g(cdiv(N, kThreads), B);
+    k_srg_label<<<g, kThreads, 0, s>>>(labels, probs, cues, th1, th2, renorm, e->lmap, e->lflag,
+                                       e->parent, e->hc, label_map_out, M, N, e->W);
+    k_srg_merge<<<g, kThreads, 0, s>>>(e->lmap, e->parent, N, e->W);
+    k_srg_flag<<<g, kThreads, 0, s>>>(e->lflag, e->parent, e->hc, N);
+    k_srg_emit<<<g, kThreads, 0, s>>>(cues, e->lmap, e->lflag, e->parent, e->hc, seeds_out, M, N);
+    e->launches += 4;
+    DSRG_CUDA_TRY(cudaGetLastError());
+    return DSRG_OK;
+}
+
+}  // namespace dsrg

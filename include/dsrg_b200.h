@@ -1,0 +1,193 @@
+/*
+ * dsrg_b200.h -- C ABI of the B200-native DSRG pixel-labelling hot path.
+ *
+ * Plain C, no torch / C++ types.  All `*_dev` pointers are CUDA device pointers on the
+ * engine's device (e.g. torch.Tensor.data_ptr()); all `*_host` pointers are host memory
+ * (pinned memory from dsrg_host_alloc() makes the copies asynchronous).  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Every function returning int
+ * returns 0 on success and a negative DSRG_E_* code on failure; dsrg_last_error() then holds a
+ * human-readable message (thread-local).  Nothing in this library falls back to a CPU path:
+ * without a usable sm_100 device every call fails with DSRG_E_CUDA.
+ *
+ * Each entry point names the reference interface (speedinghzl/DSRG, path:line) it replaces.
+ * Layout names: NHWC = [B][H][W][M] (pixel-major, what krahenbuhl2013.CRF and DenseCRFWrapper
+ * use), NCHW = [B][M][H][W] (Caffe blobs, what pylayers.py passes around).
+ */
+#ifndef DSRG_B200_H
+#define DSRG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSRG_OK 0
+#define DSRG_E_INVALID (-1)   /* bad argument (shape, layout, NULL pointer, batch > max_batch) */
+#define DSRG_E_CUDA (-2)      /* CUDA runtime error, or no sm_100 device                        */
+#define DSRG_E_KEYRANGE (-3)  /* lattice coordinates exceed the packed-key range */
+#define DSRG_E_STATE (-4)     /* call order violated (e.g. inference before add_pairwise)       */
+#define DSRG_E_NOMEM (-5)
+
+#define DSRG_LAYOUT_NHWC 0
+#define DSRG_LAYOUT_NCHW 1
+
+#define DSRG_MAX_LABELS 32 /* labels per pixel supported by the register-tiled kernels */
+
+int dsrg_version(void);               /* 10000*major + 100*minor + patch */
+const char *dsrg_last_error(void);    /* message of the last failing call on this thread */
+int dsrg_device_count(void);          /* number of visible CUDA devices (0 if none / no driver) */
+
+/* Pinned host memory so the *_host entry points overlap their copies (cudaHostAlloc). */
+void *dsrg_host_alloc(size_t bytes);
+void dsrg_host_free(void *p);
+
+/* ------------------------------------------------------------------------------------------
+ * Pairwise parameters of krahenbuhl2013.CRF -- CRF/krahenbuhl2013/CRF.py:31-32 passes
+ * (w1=10, 80/s, 80/s, 13, 13, 13, w2=3, 3/s, 3/s); argument order and meaning are those of
+ * DenseCRFWrapper::add_pairwise_energy, CRF/src/densecrf_wrapper.cpp:18-30
+ * (Gaussian/spatial kernel w2 is applied BEFORE the bilateral kernel w1).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dsrg_crf_params {
+    float w1;            /* bilateral Potts weight                     */
+    float theta_alpha_x; /* bilateral spatial sigma (x)                */
+    float theta_alpha_y; /* bilateral spatial sigma (y)                */
+    float theta_beta_r;  /* bilateral colour sigmas, channel 0 / 1 / 2 */
+    float theta_beta_g;
+    float theta_beta_b;
+    float w2;            /* spatial Potts weight                       */
+    float theta_gamma_x; /* spatial sigma (x)                          */
+    float theta_gamma_y; /* spatial sigma (y)                          */
+    int n_iters;         /* mean-field iterations (CRF.py:4 maxiter=10) */
+} dsrg_crf_params;
+
+/* Fill `p` exactly as CRF.py:31-32 does for a given scale_factor / color_factor / maxiter. */
+void dsrg_crf_params_default(dsrg_crf_params *p, float scale_factor, float color_factor, int maxiter);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine: owns every device buffer the batched kernels need for up to max_batch images of
+ * H x W pixels and M labels on `device`.  No allocation happens on the hot calls.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dsrg_engine dsrg_engine;
+
+dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M);
+void dsrg_engine_destroy(dsrg_engine *e);
+size_t dsrg_engine_device_bytes(const dsrg_engine *e); /* bytes of HBM held by the engine */
+/* Kernel launches issued by this engine since the last call (bench.py's gpu_launches). */
+long long dsrg_engine_take_launch_count(dsrg_engine *e);
+
+/*
+ * Batched dense-CRF mean-field inference; replaces the per-image loop
+ *   for i in range(N): result[i] = CRF(im[i], unary[i], scale_factor)
+ * of pylayers/pylayers/pylayers.py:81-82 / :325-326, i.e. B x { CRF.py:4-37 ->
+ * wrapper.pyx:23-60 -> densecrf_wrapper.cpp:5-50 -> DenseCRF::inference, densecrf.cpp:115-131 }.
+ *   unary : B x (H,W,M) values as passed to CRF(image, unary): energy = -unary (CRF.py:28)
+ *   image : B x (H,W,3) uint8 (CRF.py:32 casts to ubyte)
+ *   out   : B x marginals Q, float32
+ * Results are within 1e-4 (max abs) of the reference; see DESIGN.md for why not bit-exact.
+ */
+int dsrg_crf_batch_dev(dsrg_engine *e, int B, const float *unary_dev, int unary_layout,
+                       const uint8_t *image_dev, const dsrg_crf_params *params, float *out_dev,
+                       int out_layout, void *stream);
+int dsrg_crf_batch_host(dsrg_engine *e, int B, const float *unary_host, int unary_layout,
+                        const uint8_t *image_host, const dsrg_crf_params *params, float *out_host,
+                        int out_layout);
+/* arg-max labelling after inference: DenseCRFWrapper::map, densecrf_wrapper.cpp:39-43 */
+int dsrg_crf_map_batch_dev(dsrg_engine *e, int B, const float *unary_dev, int unary_layout,
+                           const uint8_t *image_dev, const dsrg_crf_params *params,
+                           int32_t *labels_out_dev, void *stream);
+
+/*
+ * Batched seeded region growing; replaces
+ *   self.pool.map(generate_seed_step, items)     pylayers/pylayers/pylayers.py:341-342
+ * = B x generate_seed_step (pylayers.py:237-275) incl. CC_labeling_8.CC_lab
+ * (pylayers/pylayers/CC_labeling_8.py:103-282).
+ *   labels : [B][M]       image-level tags, class c present iff labels[c] == 1
+ *   probs  : [B][M][H][W] float32 (compared in float64 like the reference's data)
+ *   cues   : [B][M][H][W] float32 0/1 seeds
+ *   th1,th2: background / foreground thresholds as float64 (the reference compares Python
+ *            floats 0.99 / 0.85 against float64 data with strict >)
+ *   renorm : 1 = first apply the post-CRF clamp(1e-4) + float64 renormalisation of
+ *            pylayers.py:328-330 to `probs` (the DSRGLayer path); 0 = use probs as given
+ *   seeds_out     : [B][M][H][W] float32 0/1 (old seeds are kept, pylayers.py:275)
+ *   label_map_out : optional [B][H][W] int32 (0 = none, c+1 = class c), may be NULL
+ * Bit-exact against the reference for identical inputs.
+ */
+int dsrg_srg_batch_dev(dsrg_engine *e, int B, const float *labels_dev, const float *probs_dev,
+                       const float *cues_dev, double th1, double th2, int renorm,
+                       float *seeds_out_dev, int32_t *label_map_out_dev, void *stream);
+int dsrg_srg_batch_host(dsrg_engine *e, int B, const float *labels_host, const float *probs_host,
+                        const float *cues_host, double th1, double th2, int renorm,
+                        float *seeds_out_host, int32_t *label_map_out_host);
+
+/*
+ * The whole DSRGLayer.forward body (pylayers.py:297-304, :333-344): refinement
+ * (pylayers.py:310-331: in-place clamp of probs at 1e-4, CRF with unary = probs, clamp +
+ * float64 renormalise) followed by SRG.  `image` is the already zoomed / mean-added / rounded
+ * uint8 image at the probs resolution (the host shim does pylayers.py:315-319).
+ *   probs_dev     : [B][M][H][W], CLAMPED IN PLACE like the reference's bottom blob (:312)
+ *   crf_out_dev   : optional [B][M][H][W] float32 RAW CRF marginals of this very call, i.e. before
+ *                   the clamp + float64 renormalisation of :328-330 (NULL to skip)
+ */
+int dsrg_dsrg_forward_dev(dsrg_engine *e, int B, const float *labels_dev, float *probs_dev,
+                          const float *cues_dev, const uint8_t *image_dev,
+                          const dsrg_crf_params *params, double th1, double th2,
+                          float *seeds_out_dev, float *crf_out_dev, void *stream);
+int dsrg_dsrg_forward_host(dsrg_engine *e, int B, const float *labels_host, float *probs_host,
+                           const float *cues_host, const uint8_t *image_host,
+                           const dsrg_crf_params *params, double th1, double th2,
+                           float *seeds_out_host, float *crf_out_host);
+
+/*
+ * CRFLayer.forward body (pylayers.py:63-88): same refinement, output log(result).
+ *   log_out_dev : [B][M][H][W] float32 = log(renormalised marginals)
+ *   result_dev  : optional [B][M][H][W] float32 copy of the marginals kept for backward (:90-92)
+ */
+int dsrg_crflayer_forward_dev(dsrg_engine *e, int B, float *probs_dev, const uint8_t *image_dev,
+                              const dsrg_crf_params *params, float *log_out_dev,
+                              float *result_dev, void *stream);
+
+/*
+ * BalancedSeedLossLayer (pylayers.py:120-152).  Forward writes the LOCAL sums
+ *   terms_out[0] = sum_n S_bg(n) / max(cnt_bg(n), 1e-4),  terms_out[1] = same for fg
+ * so that loss = -(terms[0] + terms[1]) / N_global; with several GPUs the two floats are
+ * all-reduced (SUM) first -- the only collective on the path.  Backward writes
+ *   grad = top_diff * d loss / d probs = -top_diff * lab / (p * max(cnt,1e-4) * N_global).
+ */
+int dsrg_seedloss_forward_dev(dsrg_engine *e, int B, const float *probs_dev,
+                              const float *seeds_dev, float *terms_out_dev, void *stream);
+int dsrg_seedloss_backward_dev(dsrg_engine *e, int B, int n_global, const float *probs_dev,
+                               const float *seeds_dev, float top_diff, float *grad_out_dev,
+                               void *stream);
+
+/* Introspection used by the lattice-level parity tests: vertex counts of the lattices built by
+ * the last CRF call (spatial, then bilateral per image). */
+int dsrg_engine_lattice_sizes(dsrg_engine *e, int B, int *v_spatial_out, int *v_bilateral_out);
+/* Per-pixel symmetric normalisation vectors (DenseKernel::norm_, pairwise.cpp:54-57) of the
+ * last CRF call: which = 0 spatial [N] (shared by the batch), 1 bilateral [B][N]. */
+int dsrg_engine_copy_norm(dsrg_engine *e, int which, int B, float *norm_out_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-object API with the exact surface of the reference's C++ class DenseCRFWrapper
+ * (CRF/include/densecrf_wrapper.h:3-28), which krahenbuhl2013/wrapper.pyx:20-60 binds.
+ * Host pointers, borrowed for the duration of the call, like the original.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dsrg_densecrf dsrg_densecrf;
+
+dsrg_densecrf *dsrg_densecrf_create(int W, int H, int nlabels);            /* densecrf_wrapper.cpp:5-8   */
+void dsrg_densecrf_destroy(dsrg_densecrf *c);                              /* :10-12                     */
+int dsrg_densecrf_npixels(const dsrg_densecrf *c);                         /* :14                        */
+int dsrg_densecrf_nlabels(const dsrg_densecrf *c);                         /* :15                        */
+int dsrg_densecrf_set_unary_energy(dsrg_densecrf *c, const float *unary_costs); /* :32-37, [N][M] energies */
+int dsrg_densecrf_add_pairwise_energy(dsrg_densecrf *c, float w1, float theta_alpha_1,
+                                      float theta_alpha_2, float theta_betta_1, float theta_betta_2,
+                                      float theta_betta_3, float w2, float theta_gamma_1,
+                                      float theta_gamma_2, const unsigned char *im);  /* :18-30 */
+int dsrg_densecrf_map(dsrg_densecrf *c, int n_iters, int *labels);         /* :39-43 */
+int dsrg_densecrf_inference(dsrg_densecrf *c, int n_iters, float *probs_out); /* :45-50 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSRG_B200_H */

@@ -1,0 +1,147 @@
+"""tests/golden/make_golden.py -- regenerates the committed golden fixtures.
+
+Runs ONLY in the dev container (needs /root/reference):
+  * SRG: the reference's own generate_seed_step + CC_labeling_8, executed in place
+    (oracle/srg_oracle.py:reference_generate_seed_step) on seeded synthetic problems
+    -> tests/golden/srg_ref_*.npz (outputs stored as packed bits; inputs are regenerated
+       from the seed by dsrg_b200/synth.py, a checksum of the inputs guards against drift)
+  * lattice: the reference's own CRF/src/permutohedral.cpp (oracle/_ref) on real feature
+    matrices -> tests/golden/lattice_ref.npz (vertex counts, exact sums / checksums of
+    offsets, barycentrics, ranks, neighbours and of seq/sse compute outputs)
+  * CRF: oracle/crf_oracle.c marginals (restatement; its lattice is pinned by the previous
+    item) -> tests/golden/crf_oracle_*.npz, so GPU runs have a frozen target even if the
+    oracle sources change later.
+
+usage: python tests/golden/make_golden.py
+"""
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from dsrg_b200 import synth  # noqa: E402
+from oracle import crf_oracle, srg_oracle  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+SRG_CASES = [  # name, H, W, cues variant, image index, tweak
+    ("a", 41, 41, "cam", 0, None),
+    ("b", 41, 41, "random", 1, None),
+    ("c", 33, 57, "random", 2, "ties"),
+    ("d", 64, 48, "cam", 3, "ties"),
+    ("e", 1, 1, "random", 4, None),
+    ("f", 1, 37, "random", 5, None),
+    ("g", 29, 1, "cam", 6, None),
+    ("h", 96, 96, "random", 7, None),
+    ("i", 321, 321, "cam", 8, None),
+    ("j", 161, 161, "random", 9, "ties"),
+]
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def srg_inputs(H, W, cues, index, tweak):
+    p = synth.make_problem(index, H, W, cues=cues, image="noise")
+    probs = p["probs"].copy()
+    if tweak == "ties":  # values exactly at the thresholds, and exact ties between classes
+        probs[:, ::3, ::2] = np.float32(0.85)
+        probs[0, 1::4, :] = np.float32(0.99)
+        probs[:, 2::5, 1::3] = np.float32(1.0 / 21)
+    return p["labels"], p["cues"], probs
+
+
+def make_srg():
+    for name, H, W, cues, index, tweak in SRG_CASES:
+        labels, cu, probs = srg_inputs(H, W, cues, index, tweak)
+        t = time.time()
+        out = srg_oracle.run_reference(labels, cu, probs, 0.99, 0.85)
+        dt = time.time() - t
+        assert set(np.unique(out)) <= {0.0, 1.0}
+        np.savez_compressed(os.path.join(OUT, "srg_ref_%s.npz" % name), H=H, W=W, cues=cues, index=index,
+                            tweak=str(tweak), th1=0.99, th2=0.85, inputs_sha256=digest(labels, cu, probs),
+                            seeds_bits=np.packbits(out.astype(np.uint8)), seeds_shape=np.array(out.shape),
+                            ref_seconds=dt)
+        print("srg", name, H, W, "ref %.2fs" % dt, int(cu.sum()), "->", int(out.sum()))
+
+
+def features(H, W, image, sx, sy, sr):
+    ys, xs = np.mgrid[0:H, 0:W]
+    d = 2 if image is None else 5
+    f = np.empty((H * W, d), np.float32)
+    f[:, 0] = xs.ravel().astype(np.float32) / np.float32(sx)
+    f[:, 1] = ys.ravel().astype(np.float32) / np.float32(sy)
+    if image is not None:
+        for c in range(3):
+            f[:, 2 + c] = image.reshape(-1, 3)[:, c].astype(np.float32) / np.float32(sr)
+    return f
+
+
+LATTICE_CASES = [  # name, H, W, image variant or None, sigma_xy, sigma_rgb
+    ("sp3_41", 41, 41, None, 3.0, 0),
+    ("sp025_41", 41, 41, None, 0.25, 0),
+    ("sp3_321", 321, 321, None, 3.0, 0),
+    ("bi_smooth_41_s12", 41, 41, "smooth", 80 / 12.0, 13),
+    ("bi_noise_57x33", 33, 57, "noise", 80.0, 13),
+    ("bi_smooth_321", 321, 321, "smooth", 80.0, 13),
+    ("bi_noise_161", 161, 161, "noise", 80.0, 13),
+]
+
+
+def make_lattice():
+    rec = {}
+    for name, H, W, var, sxy, srgb in LATTICE_CASES:
+        im = None if var is None else synth.make_image(np.random.RandomState(77), H, W, var)
+        f = features(H, W, im, sxy, sxy, srgb)
+        L = crf_oracle.RefLattice(f)
+        x = np.random.RandomState(5).rand(H * W, 21).astype(np.float32)
+        sse = L.compute(x, "sse")
+        seq = L.compute(np.ones((H * W, 1), np.float32), "seq")
+        rec[name + "/M"] = L.M
+        rec[name + "/sha_struct"] = digest(L.offset, L.bary, L.rank, L.n1, L.n2)
+        rec[name + "/sha_sse"] = digest(sse)
+        rec[name + "/sha_seq"] = digest(seq)
+        rec[name + "/seq_sum"] = float(seq.astype(np.float64).sum())
+        print("lattice", name, "M", L.M)
+    np.savez_compressed(os.path.join(OUT, "lattice_ref.npz"), **rec)
+
+
+CRF_CASES = [  # name, H, W, image variant, scale_factor, unary kind
+    ("train41_smooth", 41, 41, "smooth", 12.0, "p"),
+    ("train41_noise", 41, 41, "noise", 12.0, "p"),
+    ("test_57x33_smooth", 33, 57, "smooth", 1.0, "logp"),
+    ("test_64_noise", 64, 64, "noise", 1.0, "logp"),
+]
+
+
+def crf_inputs(H, W, var, kind, index):
+    p = synth.make_problem(100 + index, H, W, image=var)
+    pr = np.transpose(p["probs"], (1, 2, 0)).copy()
+    pr[pr < 1e-5] = 1e-5
+    unary = pr if kind == "p" else np.log(pr)
+    return p["image"], unary.astype(np.float32)
+
+
+def make_crf():
+    for i, (name, H, W, var, sf, kind) in enumerate(CRF_CASES):
+        im, unary = crf_inputs(H, W, var, kind, i)
+        q = crf_oracle.CRF(im, unary, maxiter=10, scale_factor=sf)
+        np.savez_compressed(os.path.join(OUT, "crf_oracle_%s.npz" % name), H=H, W=W, image_variant=var,
+                            scale_factor=sf, unary_kind=kind, index=i, inputs_sha256=digest(im, unary), Q=q)
+        print("crf", name, q.shape, float(q.max()))
+
+
+if __name__ == "__main__":
+    assert srg_oracle.reference_available(), "needs /root/reference"
+    crf_oracle.build(force=True)
+    make_srg()
+    make_lattice()
+    make_crf()

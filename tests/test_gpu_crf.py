@@ -1,0 +1,113 @@
+"""GPU parity: dense-CRF mean field through the C ABI vs the CPU oracle (tolerance 1e-4 max-abs on
+the marginals, BASELINE.json north_star) and vs the frozen golden vectors."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from helpers import crf_case_inputs, make_golden
+from dsrg_b200 import api, synth
+from oracle import crf_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4  # max |Q_gpu - Q_ref| (north_star: "within 1e-4 on the CRF's float marginals")
+
+
+@pytest.mark.parametrize("name", [c[0] for c in make_golden.CRF_CASES])
+def test_crf_golden_cases_object_api(torch_cuda, name):
+    """krahenbuhl2013-shaped per-image object API (host pointers) vs the frozen golden marginals."""
+    g = load_golden("crf_oracle_%s.npz" % name)
+    im, unary, sf = crf_case_inputs(name)
+    H, W, M = unary.shape
+    c = api.DenseCRF(W, H, M)
+    c.set_unary_energy(-unary.ravel().astype("float32"))
+    c.add_pairwise_energy(10, 80 / sf, 80 / sf, 13, 13, 13, 3, 3 / sf, 3 / sf, im.ravel().astype("ubyte"))
+    q = c.inference(10).reshape(H, W, M)
+    assert np.abs(q - g["Q"]).max() <= TOL
+    # map(): arg-max labels agree wherever the oracle's top-2 margin exceeds the tolerance
+    lab = c.map(10).reshape(H, W)
+    top2 = np.sort(g["Q"], -1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 4 * TOL
+    assert np.array_equal(lab[clear], g["Q"].argmax(-1)[clear])
+
+
+@pytest.mark.parametrize("H,W,sf,img,kind", [
+    (41, 41, 12.0, "smooth", "p"),      # training shape (pylayers.py:82: scale_factor=12, unary=p)
+    (41, 41, 12.0, "noise", "p"),
+    (64, 48, 1.0, "smooth", "logp"),    # test-time shape (test-ms.py:106: unary=log p)
+    (50, 75, 1.0, "noise", "logp"),
+    (97, 113, 1.0, "smooth", "logp"),
+    (5, 3, 1.0, "noise", "p"),          # tiny, N % 4 == 3 (one phantom lane)
+    (4, 4, 12.0, "smooth", "p"),        # N % 4 == 0 (no phantom lanes)
+    (1, 1, 1.0, "noise", "logp"),
+])
+def test_crf_batch_vs_oracle_both_layouts(torch_cuda, H, W, sf, img, kind):
+    torch = torch_cuda
+    B, M = 3, 21
+    batch = synth.make_batch(B, H, W, image=img, start=40)
+    pr = np.transpose(batch["probs"], (0, 2, 3, 1)).copy()
+    pr[pr < 1e-5] = 1e-5
+    unary = (pr if kind == "p" else np.log(pr)).astype(np.float32)
+    want = np.stack([crf_oracle.CRF(batch["image"][b], unary[b], 10, sf) for b in range(B)])
+    eng = api.Engine(B, H, W, M)
+    params = api.crf_params(sf)
+    d_im = torch.from_numpy(batch["image"]).cuda()
+    # NHWC in / NHWC out
+    d_un = torch.from_numpy(unary).cuda()
+    d_out = torch.empty_like(d_un)
+    eng.crf_dev(d_un, d_im, params, d_out)
+    got = d_out.cpu().numpy()
+    assert np.abs(got - want).max() <= TOL
+    # NCHW in / NCHW out
+    d_un2 = torch.from_numpy(np.ascontiguousarray(np.transpose(unary, (0, 3, 1, 2)))).cuda()
+    d_out2 = torch.empty_like(d_un2)
+    eng.crf_dev(d_un2, d_im, params, d_out2, api.LAYOUT_NCHW, api.LAYOUT_NCHW)
+    got2 = np.transpose(d_out2.cpu().numpy(), (0, 2, 3, 1))
+    assert np.abs(got2 - want).max() <= TOL
+    # host entry point (H2D/D2H inside)
+    got3 = eng.crf_host(unary, batch["image"], params)
+    assert np.abs(got3 - want).max() <= TOL
+    np.testing.assert_allclose(got.sum(-1), 1.0, atol=1e-5)
+    eng.close()
+
+
+def test_lattice_structure_matches_oracle(torch_cuda):
+    """Vertex counts (incl. the phantom tail lanes, permutohedral.cpp:196) and the symmetric
+    normalisation vectors (pairwise.cpp:54-57) against the CPU restatement."""
+    torch = torch_cuda
+    for H, W, sf, img in ((41, 41, 12.0, "smooth"), (37, 53, 1.0, "noise"), (64, 64, 1.0, "smooth")):
+        B, M = 2, 21
+        batch = synth.make_batch(B, H, W, image=img, start=7)
+        unary = np.transpose(batch["probs"], (0, 2, 3, 1)).copy()
+        eng = api.Engine(B, H, W, M)
+        d_un = torch.from_numpy(unary).cuda()
+        eng.crf_dev(d_un, torch.from_numpy(batch["image"]).cuda(), api.crf_params(sf, maxiter=1), torch.empty_like(d_un))
+        vs, vb = eng.lattice_sizes(B)
+        ns, nb = eng.norms(B)
+        for b in range(B):
+            c = crf_oracle.DenseCRF(W, H, M)
+            c.set_unary_energy(-unary[b].ravel())
+            c.add_pairwise_energy(10, 80 / sf, 80 / sf, 13, 13, 13, 3, 3 / sf, 3 / sf, batch["image"][b].ravel())
+            assert vs == c.lattice(0).M and vb[b] == c.lattice(1).M
+            np.testing.assert_allclose(ns, c.norm(0), rtol=2e-6)
+            np.testing.assert_allclose(nb[b], c.norm(1), rtol=2e-6)
+        eng.close()
+
+
+def test_crf_error_paths(torch_cuda):
+    torch = torch_cuda
+    eng = api.Engine(2, 16, 16, 21)
+    u = torch.zeros(3, 16, 16, 21, device="cuda")
+    im = torch.zeros(3, 16, 16, 3, dtype=torch.uint8, device="cuda")
+    with pytest.raises(api.DsrgError) as ei:      # batch larger than the engine
+        eng.crf_dev(u, im, api.crf_params(), torch.empty_like(u))
+    assert ei.value.code == -1
+    p = api.crf_params()
+    p.theta_alpha_x = 0.001                        # sigma so small that keys leave the packed range
+    with pytest.raises(api.DsrgError) as ei:
+        eng.crf_dev(u[:2], im[:2], p, torch.empty_like(u[:2]))
+    assert ei.value.code == -3
+    c = api.DenseCRF(8, 8, 21)
+    with pytest.raises(api.DsrgError) as ei:      # inference before add_pairwise_energy
+        c.inference(1)
+    assert ei.value.code == -4
+    eng.close()

@@ -1,0 +1,105 @@
+"""CPU tests: the oracles against the committed golden vectors (generated from the reference's
+own code by tests/golden/make_golden.py) and against each other."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from helpers import crf_case_inputs, digest, make_golden, srg_case_inputs
+from oracle import crf_oracle, loss_oracle, srg_oracle
+
+SRG_NAMES = [c[0] for c in make_golden.SRG_CASES]
+
+
+@pytest.mark.parametrize("name", SRG_NAMES)
+def test_srg_closed_form_matches_reference_golden(name):
+    g = load_golden("srg_ref_%s.npz" % name)
+    labels, cues, probs = srg_case_inputs(name)
+    assert digest(labels, cues, probs) == str(g["inputs_sha256"]), "synthetic generator drifted"
+    want = np.unpackbits(g["seeds_bits"])[: int(np.prod(g["seeds_shape"]))].reshape(g["seeds_shape"]).astype(np.float32)
+    got = srg_oracle.srg_closed_form(labels, cues, probs, float(g["th1"]), float(g["th2"]))
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", [n for n in SRG_NAMES if n not in ("i", "j", "h")])
+def test_srg_faithful_port_matches_reference_golden(name):
+    g = load_golden("srg_ref_%s.npz" % name)
+    labels, cues, probs = srg_case_inputs(name)
+    want = np.unpackbits(g["seeds_bits"])[: int(np.prod(g["seeds_shape"]))].reshape(g["seeds_shape"]).astype(np.float32)
+    got = srg_oracle.srg_faithful(labels, cues, probs, 0.99, 0.85)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.skipif(not srg_oracle.reference_available(), reason="needs /root/reference (dev container)")
+def test_srg_reference_in_place_random_sweep():
+    from dsrg_b200 import synth
+    for i in range(6):
+        p = synth.make_problem(500 + i, 19 + 3 * i, 31 - 2 * i, cues=["cam", "random"][i % 2], image="noise")
+        want = srg_oracle.run_reference(p["labels"], p["cues"], p["probs"], 0.99, 0.85)
+        assert np.array_equal(srg_oracle.srg_closed_form(p["labels"], p["cues"], p["probs"], 0.99, 0.85), want)
+        assert np.array_equal(srg_oracle.srg_faithful(p["labels"], p["cues"], p["probs"], 0.99, 0.85), want)
+
+
+@pytest.mark.parametrize("case", make_golden.LATTICE_CASES, ids=[c[0] for c in make_golden.LATTICE_CASES])
+def test_oracle_lattice_matches_reference_permutohedral_golden(case):
+    """oracle/crf_oracle.c lattice vs the golden digests of the reference's own permutohedral.cpp."""
+    from dsrg_b200 import synth
+    name, H, W, var, sxy, srgb = case
+    g = load_golden("lattice_ref.npz")
+    im = None if var is None else synth.make_image(np.random.RandomState(77), H, W, var)
+    f = make_golden.features(H, W, im, sxy, sxy, srgb)
+    L = crf_oracle.OracleLattice(f)
+    assert L.M == int(g[name + "/M"])
+    assert digest(L.offset, L.bary, L.rank, L.n1, L.n2) == str(g[name + "/sha_struct"])
+    x = np.random.RandomState(5).rand(H * W, 21).astype(np.float32)
+    assert digest(L.compute(x, "sse")) == str(g[name + "/sha_sse"])
+    assert digest(L.compute(np.ones((H * W, 1), np.float32), "seq")) == str(g[name + "/sha_seq"])
+    np.testing.assert_allclose(L.bary.sum(1), 1.0, atol=2e-6)  # barycentric weights sum to one
+
+
+@pytest.mark.skipif(not crf_oracle.ref_available(), reason="oracle/_ref not built")
+def test_oracle_lattice_bit_exact_vs_ref_so_live():
+    rng = np.random.RandomState(3)
+    for H, W, d in ((23, 31, 2), (23, 31, 5), (40, 17, 5)):
+        f = (rng.rand(H * W, d) * [3, 3, 19, 19, 19][:d]).astype(np.float32)
+        a, b = crf_oracle.OracleLattice(f), crf_oracle.RefLattice(f)
+        assert a.M == b.M
+        for k in ("offset", "bary", "rank", "n1", "n2"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), k
+        x = rng.rand(H * W, 21).astype(np.float32)
+        assert np.array_equal(a.compute(x, "sse"), b.compute(x, "dispatch"))
+
+
+@pytest.mark.parametrize("name", [c[0] for c in make_golden.CRF_CASES])
+def test_crf_oracle_matches_frozen_golden(name):
+    g = load_golden("crf_oracle_%s.npz" % name)
+    im, unary, sf = crf_case_inputs(name)
+    assert digest(im, unary) == str(g["inputs_sha256"])
+    q = crf_oracle.CRF(im, unary, maxiter=10, scale_factor=sf)
+    np.testing.assert_allclose(q, g["Q"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(q.sum(-1), 1.0, atol=1e-5)
+
+
+def test_crf_oracle_map_and_object_api():
+    im, unary, sf = crf_case_inputs("train41_smooth")
+    H, W, M = unary.shape
+    c = crf_oracle.DenseCRF(W, H, M)
+    c.set_unary_energy(-unary.ravel())
+    c.add_pairwise_energy(10, 80 / sf, 80 / sf, 13, 13, 13, 3, 3 / sf, 3 / sf, im.ravel())
+    q = c.inference(5).reshape(H, W, M)
+    assert np.array_equal(c.map(5).reshape(H, W), q.argmax(-1))
+    assert c.lattice(0).M > 0 and c.norm(1).shape == (H * W,)
+
+
+def test_loss_oracle_gradient_is_consistent():
+    rng = np.random.RandomState(0)
+    p = rng.rand(2, 5, 6, 7) * 0.9 + 0.05
+    lab = (rng.rand(2, 5, 6, 7) < 0.2).astype(np.float64)
+    lab[1, 1:] = 0  # an image without foreground seeds: max(count, 1e-4) branch
+    g = loss_oracle.balanced_seed_loss_grad(p, lab)
+    eps = 1e-6
+    for idx in [(0, 0, 1, 2), (0, 3, 2, 2), (1, 0, 5, 6)]:
+        pp, pm = p.copy(), p.copy()
+        pp[idx] += eps
+        pm[idx] -= eps
+        num = (loss_oracle.balanced_seed_loss(pp, lab) - loss_oracle.balanced_seed_loss(pm, lab)) / (2 * eps)
+        assert abs(num - g[idx]) < 1e-5
