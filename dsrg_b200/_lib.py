@@ -51,6 +51,10 @@ SIGNATURES = {
     "dsrg_crflayer_forward_dev": (_i, [_vp, _i, _vp, _vp, _pp, _vp, _vp, _vp]),
     "dsrg_seedloss_forward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "dsrg_seedloss_backward_dev": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
+    "dsrg_profile_tag_count": (_i, []),
+    "dsrg_profile_tag_name": (C.c_char_p, [_i]),
+    "dsrg_engine_profile": (_i, [_vp, _i]),
+    "dsrg_engine_profile_read": (_i, [_vp, _vp, _vp]),
     "dsrg_engine_lattice_sizes": (_i, [_vp, _i, _vp, _vp]),
     "dsrg_engine_copy_norm": (_i, [_vp, _i, _i, _vp]),
     "dsrg_densecrf_create": (_vp, [_i, _i, _i]),
@@ -70,6 +74,12 @@ def lib():
     """Load libdsrg_b200.so (built by dsrg_b200/build.py).  Raises if it does not exist."""
     global _LIB
     if _LIB is None:
+        try:  # a stale .so silently tests yesterday's kernels: rebuild when a source is newer
+            from . import build as _build
+            if _build.needs_build():
+                _build.build()
+        except Exception:  # no nvcc here: fall through to whatever was prebuilt
+            pass
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 "%s is missing: the CUDA extension was not built (run `python -m dsrg_b200.build` "

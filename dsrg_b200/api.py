@@ -156,6 +156,18 @@ class Engine(object):
                                              _hptr(crf_out, np.float32)))
         return seeds_out
 
+    # ---- per-kernel timing ----
+    def profile(self, enable):
+        check(self._L.dsrg_engine_profile(self.h, int(bool(enable))))
+
+    def profile_read(self):
+        """{kernel class: (total ms, launches)} since the last read (synchronises the device)."""
+        n = self._L.dsrg_profile_tag_count()
+        ms = np.zeros(n, np.float32)
+        cnt = np.zeros(n, np.int64)
+        check(self._L.dsrg_engine_profile_read(self.h, _hptr(ms, np.float32), _hptr(cnt, np.int64)))
+        return {self._L.dsrg_profile_tag_name(t).decode(): (float(ms[t]), int(cnt[t])) for t in range(n) if cnt[t]}
+
     # ---- introspection ----
     def lattice_sizes(self, B):
         vs = np.zeros(1, np.int32)

@@ -302,6 +302,11 @@ void dsrg_engine_destroy(dsrg_engine *h) {
                     e->st_cues, e->st_labels, e->st_image, e->st_lmap};
     for (void *p : ptrs) cudaFree(p);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    for (auto &r : e->prof_recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto ev : e->prof_pool) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -313,6 +318,44 @@ long long dsrg_engine_take_launch_count(dsrg_engine *h) {
     long long n = e->launches;
     e->launches = 0;
     return n;
+}
+
+static const char *kTagNames[T_COUNT] = {
+    "lattice_insert", "lattice_misc", "lattice_norm", "mf_init", "mf_zero", "mf_splat", "mf_blur_spatial",
+    "mf_blur_bilateral", "mf_slice_update", "mf_export", "srg_label", "srg_merge", "srg_flag", "srg_emit",
+    "seedloss"};
+
+int dsrg_profile_tag_count(void) { return T_COUNT; }
+
+const char *dsrg_profile_tag_name(int tag) { return (tag >= 0 && tag < T_COUNT) ? kTagNames[tag] : ""; }
+
+int dsrg_engine_profile(dsrg_engine *h, int enable) {
+    Engine *e = (Engine *)h;
+    if (!e) return DSRG_E_INVALID;
+    e->prof = enable != 0;
+    return DSRG_OK;
+}
+
+int dsrg_engine_profile_read(dsrg_engine *h, float *ms_out, long long *count_out) {
+    Engine *e = (Engine *)h;
+    if (!e || !ms_out || !count_out) return DSRG_E_INVALID;
+    DSRG_CUDA_TRY(cudaSetDevice(e->device));
+    DSRG_CUDA_TRY(cudaDeviceSynchronize());
+    for (int t = 0; t < T_COUNT; t++) {
+        ms_out[t] = 0.0f;
+        count_out[t] = 0;
+    }
+    for (auto &r : e->prof_recs) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ms_out[r.tag] += ms;
+            count_out[r.tag] += 1;
+        }
+        e->prof_pool.push_back(r.a);
+        e->prof_pool.push_back(r.b);
+    }
+    e->prof_recs.clear();
+    return DSRG_OK;
 }
 
 int dsrg_crf_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layout,

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "../../include/dsrg_b200.h"
 
 namespace dsrg {
@@ -56,6 +58,13 @@ struct Lattice {
 
 struct Engine;
 
+// kernel classes for the optional per-kernel CUDA-event timing (bench.py's roofline leg)
+enum KTag {
+    T_LAT_INSERT = 0, T_LAT_MISC, T_LAT_NORM, T_MF_INIT, T_MF_ZERO, T_MF_SPLAT, T_MF_BLUR_SP,
+    T_MF_BLUR_BI, T_MF_SLICE, T_MF_EXPORT, T_SRG_LABEL, T_SRG_MERGE, T_SRG_FLAG, T_SRG_EMIT,
+    T_LOSS, T_COUNT
+};
+
 // ---- lattice.cu ----
 int lattice_build(Engine *e, Lattice &L, int B, const uint8_t *image_dev, cudaStream_t s);
 // ---- meanfield.cu ----
@@ -104,7 +113,48 @@ struct Engine {
     int32_t *st_lmap = nullptr;
     cudaStream_t own_stream = nullptr;
     int *dev_err = nullptr;  // device-side error flag
+    // per-kernel event timing (off by default)
+    bool prof = false;
+    struct ProfRec { int tag; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
 };
+
+// RAII bracket around one kernel launch: counts it and, when profiling is on, times it with a pair
+// of CUDA events on the launching stream.
+struct LaunchScope {
+    Engine *e;
+    cudaStream_t s;
+    cudaEvent_t b = nullptr;
+    LaunchScope(Engine *e_, int tag, cudaStream_t s_) : e(e_), s(s_) {
+        e->launches++;
+        if (e->prof) {
+            cudaEvent_t a = take();
+            b = take();
+            cudaEventRecord(a, s);
+            e->prof_recs.push_back({tag, a, b});
+        }
+    }
+    ~LaunchScope() {
+        if (b) cudaEventRecord(b, s);
+    }
+    cudaEvent_t take() {
+        if (!e->prof_pool.empty()) {
+            cudaEvent_t ev = e->prof_pool.back();
+            e->prof_pool.pop_back();
+            return ev;
+        }
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        return ev;
+    }
+};
+#define DSRG_LAUNCH(e, tag, s, ...)          \
+    do {                                     \
+        dsrg::LaunchScope _ls((e), (tag), (s)); \
+        __VA_ARGS__;                         \
+    } while (0)
+
 
 int device_alloc(Engine *e, void **p, size_t bytes);
 template <typename T>

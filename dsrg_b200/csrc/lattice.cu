@@ -362,15 +362,15 @@ static int build_impl(Engine *e, Lattice &L, int nb, const uint8_t *image, cudaS
     a.err = e->dev_err;
     DSRG_CUDA_TRY(cudaMemsetAsync(L.vcount, 0, sizeof(int32_t) * nb, s));
     dim3 gp(cdiv(L.N + L.P, kThreads), nb);
-    k_lattice_insert<D><<<gp, kThreads, 0, s>>>(a);
-    k_rowbase<<<1, 32, 0, s>>>(L.vcount, L.rowbase, L.shared ? e->maxB : nb, L.shared);
+    DSRG_LAUNCH(e, T_LAT_INSERT, s, k_lattice_insert<D><<<gp, kThreads, 0, s>>>(a));
+    DSRG_LAUNCH(e, T_LAT_MISC, s, k_rowbase<<<1, 32, 0, s>>>(L.vcount, L.rowbase, L.shared ? e->maxB : nb, L.shared));
     dim3 gf(cdiv((long long)(D + 1) * L.N, kThreads), nb);
-    k_lattice_finalize<<<gf, kThreads, 0, s>>>(L.off, L.hval, L.N, D + 1, a.cap);
+    DSRG_LAUNCH(e, T_LAT_MISC, s, k_lattice_finalize<<<gf, kThreads, 0, s>>>(L.off, L.hval, L.N, D + 1, a.cap));
     dim3 gv(2 * e->sm_count, nb);
-    k_lattice_neighbors<D><<<gv, kThreads, 0, s>>>(L.hkeys, L.hval, L.vslot, L.vcount, L.rowbase,
-                                                   L.nbr, L.nbr_stride, a.cap, L.capv, L.shared);
-    k_lattice_cleanup<<<gv, kThreads, 0, s>>>(L.hkeys, L.vslot, L.vcount, a.cap, L.capv);
-    e->launches += 5;
+    DSRG_LAUNCH(e, T_LAT_MISC, s,
+                k_lattice_neighbors<D><<<gv, kThreads, 0, s>>>(L.hkeys, L.hval, L.vslot, L.vcount, L.rowbase,
+                                                               L.nbr, L.nbr_stride, a.cap, L.capv, L.shared));
+    DSRG_LAUNCH(e, T_LAT_MISC, s, k_lattice_cleanup<<<gv, kThreads, 0, s>>>(L.hkeys, L.vslot, L.vcount, a.cap, L.capv));
     return DSRG_OK;
 }
 
@@ -385,18 +385,18 @@ int lattice_build(Engine *e, Lattice &L, int B, const uint8_t *image_dev, cudaSt
     const long long rows_nb = L.shared ? (long long)L.capv + 1 : L.rows_cap;
     DSRG_CUDA_TRY(cudaMemsetAsync(e->nvA, 0, sizeof(float) * rows_nb, s));
     dim3 gp(cdiv(L.N, kThreads), nb);
-    k_norm_splat<<<gp, kThreads, 0, s>>>(L.off, L.bary, L.rowbase, e->nvA, L.N, dp1);
+    DSRG_LAUNCH(e, T_LAT_NORM, s, k_norm_splat<<<gp, kThreads, 0, s>>>(L.off, L.bary, L.rowbase, e->nvA, L.N, dp1));
     float *src = e->nvA, *dst = e->nvB;
     for (int j = 0; j < dp1; j++) {
-        k_norm_blur<<<4 * e->sm_count, kThreads, 0, s>>>(src, dst, L.nbr + (size_t)j * L.nbr_stride,
-                                                          L.rowbase, nb);
+        DSRG_LAUNCH(e, T_LAT_NORM, s,
+                    k_norm_blur<<<4 * e->sm_count, kThreads, 0, s>>>(src, dst, L.nbr + (size_t)j * L.nbr_stride,
+                                                                      L.rowbase, nb));
         float *t = src;
         src = dst;
         dst = t;
     }
     const float alpha = 1.0f / (1 + powf(2, -L.d));  // permutohedral.cpp:510
-    k_norm_slice<<<gp, kThreads, 0, s>>>(L.off, L.bary, L.rowbase, src, L.norm, L.N, dp1, alpha);
-    e->launches += 2 + dp1;
+    DSRG_LAUNCH(e, T_LAT_NORM, s, k_norm_slice<<<gp, kThreads, 0, s>>>(L.off, L.bary, L.rowbase, src, L.norm, L.N, dp1, alpha));
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }

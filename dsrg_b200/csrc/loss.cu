@@ -104,9 +104,8 @@ int seedloss_forward(Engine *e, int B, const float *probs, const float *seeds, f
                      cudaStream_t s) {
     DSRG_CUDA_TRY(cudaMemsetAsync(e->loss_acc, 0, sizeof(double) * 4 * B, s));
     dim3 g(cdiv((long long)e->M * e->N, kThreads * 8), B);
-    k_seedloss_partial<<<g, kThreads, 0, s>>>(probs, seeds, e->loss_acc, e->M, e->N);
-    k_seedloss_final<<<1, 32, 0, s>>>(e->loss_acc, terms_out, B);
-    e->launches += 2;
+    DSRG_LAUNCH(e, T_LOSS, s, k_seedloss_partial<<<g, kThreads, 0, s>>>(probs, seeds, e->loss_acc, e->M, e->N));
+    DSRG_LAUNCH(e, T_LOSS, s, k_seedloss_final<<<1, 32, 0, s>>>(e->loss_acc, terms_out, B));
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }
@@ -115,10 +114,10 @@ int seedloss_backward(Engine *e, int B, int n_global, const float *probs, const 
                       float top_diff, float *grad, cudaStream_t s) {
     DSRG_CUDA_TRY(cudaMemsetAsync(e->loss_acc, 0, sizeof(double) * 4 * B, s));
     dim3 g(cdiv((long long)e->M * e->N, kThreads * 8), B);
-    k_seedloss_counts<<<g, kThreads, 0, s>>>(seeds, e->loss_acc, e->M, e->N);
-    k_seedloss_grad<<<g, kThreads, 0, s>>>(probs, seeds, e->loss_acc, top_diff / (float)n_global, grad,
-                                           e->M, e->N);
-    e->launches += 2;
+    DSRG_LAUNCH(e, T_LOSS, s, k_seedloss_counts<<<g, kThreads, 0, s>>>(seeds, e->loss_acc, e->M, e->N));
+    DSRG_LAUNCH(e, T_LOSS, s,
+                k_seedloss_grad<<<g, kThreads, 0, s>>>(probs, seeds, e->loss_acc, top_diff / (float)n_global, grad,
+                                                       e->M, e->N));
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }

@@ -284,37 +284,40 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
                     const dsrg_crf_params &p, cudaStream_t s) {
     const int M = e->M, N = e->N;
     dim3 gp(cdiv(N, kThreads), B);
-    k_mf_init<MP><<<gp, kThreads, 0, s>>>(unary, unary_rw, layout, clamp ? 1 : 0, e->U, e->Q0, M, N);
-    e->launches += 1;
+    DSRG_LAUNCH(e, T_MF_INIT, s, k_mf_init<MP><<<gp, kThreads, 0, s>>>(unary, unary_rw, layout, clamp ? 1 : 0, e->U, e->Q0, M, N));
     float *Qc = e->Q0, *Qn = e->Q1;
     const float alpha_sp = 1.0f / (1 + powf(2, -e->sp.d));  // permutohedral.cpp:571
     const float alpha_bi = 1.0f / (1 + powf(2, -e->bi.d));
     const int blur_grid = 8 * e->sm_count;
     for (int it = 0; it < p.n_iters; it++) {
         // the row counts live on the device only (no host sync on the path)
-        k_mf_zero<MP><<<blur_grid, kThreads, 0, s>>>((float4 *)e->spA, e->sp.rowbase, (float4 *)e->biA,
-                                                     e->bi.rowbase, B);
-        k_mf_splat<MP><<<gp, kThreads, 0, s>>>(Qc, make_view(e->sp, e->spA), make_view(e->bi, e->biA), M, N);
+        DSRG_LAUNCH(e, T_MF_ZERO, s,
+                    k_mf_zero<MP><<<blur_grid, kThreads, 0, s>>>((float4 *)e->spA, e->sp.rowbase, (float4 *)e->biA,
+                                                                 e->bi.rowbase, B));
+        DSRG_LAUNCH(e, T_MF_SPLAT, s,
+                    k_mf_splat<MP><<<gp, kThreads, 0, s>>>(Qc, make_view(e->sp, e->spA), make_view(e->bi, e->biA), M, N));
         float *src = e->spA, *dst = e->spB;
         for (int j = 0; j <= e->sp.d; j++) {
-            k_mf_blur<MP><<<blur_grid, kThreads, 0, s>>>((const float4 *)src, (float4 *)dst,
-                                                         e->sp.nbr + (size_t)j * e->sp.nbr_stride,
-                                                         e->sp.rowbase, B, 1);
+            DSRG_LAUNCH(e, T_MF_BLUR_SP, s,
+                        k_mf_blur<MP><<<blur_grid, kThreads, 0, s>>>((const float4 *)src, (float4 *)dst,
+                                                                     e->sp.nbr + (size_t)j * e->sp.nbr_stride,
+                                                                     e->sp.rowbase, B, 1));
             float *t = src; src = dst; dst = t;
         }
         float *sp_final = src;
         src = e->biA; dst = e->biB;
         for (int j = 0; j <= e->bi.d; j++) {
-            k_mf_blur<MP><<<blur_grid, kThreads, 0, s>>>((const float4 *)src, (float4 *)dst,
-                                                         e->bi.nbr + (size_t)j * e->bi.nbr_stride,
-                                                         e->bi.rowbase, B, 0);
+            DSRG_LAUNCH(e, T_MF_BLUR_BI, s,
+                        k_mf_blur<MP><<<blur_grid, kThreads, 0, s>>>((const float4 *)src, (float4 *)dst,
+                                                                     e->bi.nbr + (size_t)j * e->bi.nbr_stride,
+                                                                     e->bi.rowbase, B, 0));
             float *t = src; src = dst; dst = t;
         }
         float *bi_final = src;
-        k_mf_slice_update<MP><<<gp, kThreads, 0, s>>>(e->U, Qn, make_view(e->sp, sp_final),
-                                                      make_view(e->bi, bi_final), p.w2, p.w1,
-                                                      alpha_sp, alpha_bi, M, N);
-        e->launches += 3 + (e->sp.d + 1) + (e->bi.d + 1);
+        DSRG_LAUNCH(e, T_MF_SLICE, s,
+                    k_mf_slice_update<MP><<<gp, kThreads, 0, s>>>(e->U, Qn, make_view(e->sp, sp_final),
+                                                                  make_view(e->bi, bi_final), p.w2, p.w1,
+                                                                  alpha_sp, alpha_bi, M, N));
         float *t = Qc; Qc = Qn; Qn = t;
     }
     e->Qcur = Qc;
@@ -340,24 +343,21 @@ int meanfield_run(Engine *e, int B, const float *unary, int unary_layout, bool c
 
 int meanfield_export(Engine *e, int B, float *out, int layout, cudaStream_t s) {
     dim3 gp(cdiv(e->N, kThreads), B);
-    k_mf_export<<<gp, kThreads, 0, s>>>(e->Qcur, out, layout, e->M, e->N);
-    e->launches += 1;
+    DSRG_LAUNCH(e, T_MF_EXPORT, s, k_mf_export<<<gp, kThreads, 0, s>>>(e->Qcur, out, layout, e->M, e->N));
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }
 
 int meanfield_export_map(Engine *e, int B, int32_t *labels, cudaStream_t s) {
     dim3 gp(cdiv(e->N, kThreads), B);
-    k_mf_export_map<<<gp, kThreads, 0, s>>>(e->Qcur, labels, e->M, e->N);
-    e->launches += 1;
+    DSRG_LAUNCH(e, T_MF_EXPORT, s, k_mf_export_map<<<gp, kThreads, 0, s>>>(e->Qcur, labels, e->M, e->N));
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }
 
 int meanfield_export_renorm(Engine *e, int B, float *result_out, float *log_out, cudaStream_t s) {
     dim3 gp(cdiv(e->N, kThreads), B);
-    k_mf_export_renorm<<<gp, kThreads, 0, s>>>(e->Qcur, result_out, log_out, e->M, e->N);
-    e->launches += 1;
+    DSRG_LAUNCH(e, T_MF_EXPORT, s, k_mf_export_renorm<<<gp, kThreads, 0, s>>>(e->Qcur, result_out, log_out, e->M, e->N));
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }

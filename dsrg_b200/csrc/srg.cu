@@ -182,12 +182,13 @@ int srg_run(Engine *e, int B, const float *labels, const float *probs, const flo
             cudaStream_t s) {
     const int N = e->N, M = e->M;
     dim3 g(cdiv(N, kThreads), B);
-    k_srg_label<<<g, kThreads, 0, s>>>(labels, probs, cues, th1, th2, renorm, e->lmap, e->lflag,
-                                       e->parent, e->hc, label_map_out, M, N, e->W);
-    k_srg_merge<<<g, kThreads, 0, s>>>(e->lmap, e->parent, N, e->W);
-    k_srg_flag<<<g, kThreads, 0, s>>>(e->lflag, e->parent, e->hc, N);
-    k_srg_emit<<<g, kThreads, 0, s>>>(cues, e->lmap, e->lflag, e->parent, e->hc, seeds_out, M, N);
-    e->launches += 4;
+    DSRG_LAUNCH(e, T_SRG_LABEL, s,
+                k_srg_label<<<g, kThreads, 0, s>>>(labels, probs, cues, th1, th2, renorm, e->lmap, e->lflag,
+                                                   e->parent, e->hc, label_map_out, M, N, e->W));
+    DSRG_LAUNCH(e, T_SRG_MERGE, s, k_srg_merge<<<g, kThreads, 0, s>>>(e->lmap, e->parent, N, e->W));
+    DSRG_LAUNCH(e, T_SRG_FLAG, s, k_srg_flag<<<g, kThreads, 0, s>>>(e->lflag, e->parent, e->hc, N));
+    DSRG_LAUNCH(e, T_SRG_EMIT, s,
+                k_srg_emit<<<g, kThreads, 0, s>>>(cues, e->lmap, e->lflag, e->parent, e->hc, seeds_out, M, N));
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }

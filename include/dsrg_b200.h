@@ -161,6 +161,15 @@ int dsrg_seedloss_backward_dev(dsrg_engine *e, int B, int n_global, const float 
                                const float *seeds_dev, float top_diff, float *grad_out_dev,
                                void *stream);
 
+/* Optional per-kernel timing for the roofline report: while enabled every kernel launch of the
+ * engine is bracketed by CUDA events on its launching stream.  dsrg_engine_profile_read()
+ * synchronises the device and returns, per kernel class (dsrg_profile_tag_count() of them, named by
+ * dsrg_profile_tag_name()), the summed milliseconds and the number of launches since the last read. */
+int dsrg_profile_tag_count(void);
+const char *dsrg_profile_tag_name(int tag);
+int dsrg_engine_profile(dsrg_engine *e, int enable);
+int dsrg_engine_profile_read(dsrg_engine *e, float *ms_out, long long *count_out);
+
 /* Introspection used by the lattice-level parity tests: vertex counts of the lattices built by
  * the last CRF call (spatial, then bilateral per image). */
 int dsrg_engine_lattice_sizes(dsrg_engine *e, int B, int *v_spatial_out, int *v_bilateral_out);
