@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the DSRG pixel-labelling hot path (BASELINE.json metric:
+images/s for the SRG + DenseCRF pass at 321x321x21).
+
+One "step" = one pass of the hot path over one batch of synthetic images:
+  dsrg321 (default): DSRGLayer.forward body = dense-CRF refinement (10 mean-field iterations,
+                     bilateral 80/13 + spatial 3, unary = probs) -> float64 clamp/renormalise ->
+                     seeded region growing (th 0.99/0.85), batch 64 @ 321x321x21
+  crf321 / srg321  : the CRF-only / SRG-only configurations of BASELINE.json (batch 64)
+  full513          : the same full pass + balanced seeding loss, batch 16 @ 513x513x21
+
+`python bench.py --gpus N --steps K --warmup W` prints ONE JSON line (rank 0).  Under torchrun
+(WORLD_SIZE > 1) every rank runs the same per-rank batch on its own GPU (images shard with no
+data-path collective; weak scaling) and the time is the max over ranks.
+
+`--impl reference` times the reference's CPU path instead (oracle port: oracle/crf_oracle.c +
+oracle/srg_oracle.py:srg_faithful) on all host cores; this and the `cpu_baseline` leg are the only
+places bench.py touches oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    #            H    W    B   what
+    "dsrg321": (321, 321, 64, "crf+srg"),
+    "crf321": (321, 321, 64, "crf"),
+    "srg321": (321, 321, 64, "srg"),
+    "full513": (513, 513, 16, "crf+srg+loss"),
+}
+M = 21
+T_ITERS = 10
+TH1, TH2 = 0.99, 0.85
+
+
+def algorithmic_bytes_per_image(what, N):
+    """compulsory dense-array traffic per image."""
+    b_srg = 252 * N                          # probs + cues in, seeds out: 3 * 4*C*N
+    b_crf = N * (3 + 8 * M + 12 * M * T_ITERS)
+    b_loss = 2 * 4 * M * N
+    return {"crf": b_crf, "srg": b_srg, "crf+srg": b_crf + b_srg, "crf+srg+loss": b_crf + b_srg + b_loss}[what]
+
+
+def kernel_algorithmic_bytes(tag, N, B):
+    """Algorithmic bytes ONE launch of a kernel class moves for a batch of B images."""
+    per = {
+        "mf_slice_update": 8 * M * N,   # read U, write Q
+        "mf_splat": 4 * M * N,          # read Q
+        "mf_init": 8 * M * N + 4 * M * N,
+        "srg_label": 8 * M * N,         # probs + cues
+        "srg_emit": 4 * M * N,          # seeds out
+        "mf_export": 8 * M * N,
+    }
+    return per.get(tag, 0) * B
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(object):
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def synth_batch(H, W, B, unique=8):
+    from dsrg_b200 import synth
+    return synth.make_batch(B, H, W, cues="cam", image="smooth", unique=unique)
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path (oracle port) -- also the cpu_baseline leg
+# --------------------------------------------------------------------------------------------
+def _cpu_one(args):
+    what, labels, probs, cues, image = args
+    from oracle import crf_oracle, loss_oracle, srg_oracle
+    probs = probs.copy()
+    out = None
+    if "crf" in what:
+        # refinement() with the image already at map resolution: pylayers.py:310-331 minus the zoom
+        probs[probs < crf_oracle.MIN_PROB] = crf_oracle.MIN_PROB
+        unary = np.ascontiguousarray(np.transpose(probs, (1, 2, 0)))
+        q = crf_oracle.CRF(image, unary, maxiter=T_ITERS, scale_factor=1.0)
+        r = np.transpose(np.array(q, np.float64), (2, 0, 1))
+        r[r < crf_oracle.MIN_PROB] = crf_oracle.MIN_PROB
+        r = r / np.sum(r, axis=0, keepdims=True)
+        out = r
+    if "srg" in what:
+        src = out if out is not None else probs.astype(np.float64)
+        out = srg_oracle.srg_faithful(labels, cues, src, TH1, TH2)
+    if "loss" in what:
+        loss_oracle.balanced_seed_loss(probs[None], out[None], np.float32)
+    return float(np.sum(out))
+
+
+def cpu_images_per_second(what, batch, n_images, cores):
+    items = [(what, batch["labels"][i % len(batch["labels"])], batch["probs"][i % len(batch["probs"])],
+              batch["cues"][i % len(batch["cues"])], batch["image"][i % len(batch["image"])]) for i in range(n_images)]
+    t = time.perf_counter()
+    if cores == 1:
+        for it in items:
+            _cpu_one(it)
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(cores) as pool:  # the reference fans SRG out with Pool() (pylayers.py:292,342)
+            pool.map(_cpu_one, items, chunksize=1)
+    dt = time.perf_counter() - t
+    return n_images / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import crf_oracle
+    crf_oracle.build()
+    H, W, B, what = WORKLOADS[args.workload]
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    cores = max(1, min(cores, 64))  # every host thread we may use, capped at the batch size (26 MB pickled per image)
+    n = cores  # one image per core per step: a bounded sample of the batch-64 workload
+    batch = synth_batch(H, W, min(n, 8), unique=8)
+    for _ in range(args.warmup):
+        cpu_images_per_second(what, batch, min(n, 2), min(cores, 2))
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_images_per_second(what, batch, n, cores)
+    dt = time.perf_counter() - t
+    value = n * args.steps / dt
+    sample = "%d images/step (1 per host thread) of the %s workload, %d steps, multiprocessing.Pool(%d)" % (n, args.workload, args.steps, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "images/s, SRG + DenseCRF pass at %dx%dx%d" % (H, W, M), "value": value,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "what": what, "H": H, "W": W, "labels": M, "mean_field_iters": T_ITERS,
+                   "images_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    from dsrg_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    H, W, B, what = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    N = H * W
+    batch = synth_batch(H, W, B)
+    dev = torch.device("cuda", local_rank)
+    eng = api.Engine(B, H, W, M, device=local_rank)
+    params = api.crf_params(1.0, 13, T_ITERS)
+    d_labels = torch.from_numpy(batch["labels"]).to(dev)
+    d_probs = torch.from_numpy(batch["probs"]).to(dev)
+    d_cues = torch.from_numpy(batch["cues"]).to(dev)
+    d_image = torch.from_numpy(batch["image"]).to(dev)
+    d_seeds = torch.empty_like(d_probs)
+    d_unary = d_probs.permute(0, 2, 3, 1).contiguous() if what == "crf" else None   # one-off layout prep, untimed
+    d_q = torch.empty_like(d_unary) if what == "crf" else None
+    d_terms = torch.zeros(2, device=dev)
+
+    def step():
+        if what == "crf":
+            eng.crf_dev(d_unary, d_image, params, d_q)
+        elif what == "srg":
+            eng.srg_dev(d_labels, d_probs, d_cues, TH1, TH2, d_seeds)
+        else:
+            eng.dsrg_forward_dev(d_labels, d_probs, d_cues, d_image, params, TH1, TH2, d_seeds)
+            if "loss" in what:
+                eng.seedloss_forward_dev(d_probs, d_seeds, d_terms)
+                if dist is not None:
+                    dist.all_reduce(d_terms)   # the path's only collective: 2 floats
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    eng.take_launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms = timed(step, args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.take_launch_count()
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # per-kernel durations by CUDA events on the launching stream, same K steps repeated
+    eng.profile(True)
+    ms_prof = timed(step, args.steps)
+    prof = eng.profile_read()
+    eng.profile(False)
+    peak, peak_src = measured_peak()
+    total_kernel_ms = sum(v[0] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
+    roofline = None
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                   "share": v[0] / total_kernel_ms} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    if top:
+        tag, (tms, cnt) = top
+        per_launch_s = tms * 1e-3 / cnt
+        ab = kernel_algorithmic_bytes(tag, N, B)
+        ach = ab / per_launch_s / 1e9 if ab else 0.0
+        roofline = {"bound": "hbm", "kernel": tag, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                    "avg_launch_ms": per_launch_s * 1e3, "share_of_step": tms / total_kernel_ms,
+                    "step_algorithmic_GBs": algorithmic_bytes_per_image(what, N) * B * args.steps / (ms * 1e-3) / 1e9,
+                    "step_frac": algorithmic_bytes_per_image(what, N) * B * args.steps / (ms * 1e-3) / 1e9 / peak,
+                    "profiled_ms_per_step": ms_prof / args.steps}
+
+    # end to end through the host-buffer C-ABI entry point (pinned host memory, copies inside)
+    e2e = None
+    if what in ("crf+srg", "crf+srg+loss", "srg", "crf"):
+        h_labels = api.pinned_empty(batch["labels"].shape, np.float32); h_labels[...] = batch["labels"]
+        h_probs = api.pinned_empty(batch["probs"].shape, np.float32); h_probs[...] = batch["probs"]
+        h_cues = api.pinned_empty(batch["cues"].shape, np.float32); h_cues[...] = batch["cues"]
+        h_image = api.pinned_empty(batch["image"].shape, np.uint8); h_image[...] = batch["image"]
+        h_seeds = api.pinned_empty(batch["probs"].shape, np.float32)
+        if what == "crf":
+            h_unary = api.pinned_empty((B, H, W, M), np.float32); h_unary[...] = np.transpose(batch["probs"], (0, 2, 3, 1))
+            h_q = api.pinned_empty((B, H, W, M), np.float32)
+
+            def host_step():
+                eng.crf_host(h_unary, h_image, params, out=h_q)
+            h2d, d2h = h_unary.nbytes + h_image.nbytes, h_q.nbytes
+        elif what == "srg":
+            def host_step():
+                eng.srg_host(h_labels, h_probs, h_cues, TH1, TH2, seeds_out=h_seeds)
+            h2d, d2h = h_labels.nbytes + h_probs.nbytes + h_cues.nbytes, h_seeds.nbytes
+        else:
+            def host_step():
+                eng.dsrg_forward_host(h_labels, h_probs, h_cues, h_image, params, TH1, TH2, seeds_out=h_seeds)
+            h2d = h_labels.nbytes + h_probs.nbytes + h_cues.nbytes + h_image.nbytes
+            d2h = h_seeds.nbytes + h_probs.nbytes   # seeds + the in-place-clamped probs blob
+        for _ in range(2):
+            host_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_step()          # synchronises its own stream before returning
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * B * args.steps / dt, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "api": "dsrg_*_host (C ABI, pinned host buffers)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import crf_oracle
+        crf_oracle.build()
+        n = 6
+        v, dt = cpu_images_per_second(what, batch, n, 1)
+        cpu_baseline = {"value": v, "unit": "images/s", "cores": 1, "kind": "port",
+                        "sample": "%d images of the same %s batch, single thread like the reference's serial CRF loop "
+                                  "(pylayers.py:325-326); %.1f s of CPU work" % (n, args.workload, dt)}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "images/s, SRG + DenseCRF pass at %dx%dx%d" % (H, W, M), "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "what": what, "H": H, "W": W, "labels": M, "batch_per_gpu": B,
+                       "global_batch": B * world, "mean_field_iters": T_ITERS, "sigma": "bilateral 80/13, spatial 3",
+                       "thresholds": [TH1, TH2], "images": "smooth, cam-like cues, 8 distinct images repeated",
+                       "l2": "inputs larger than L2 (%.0f MB of probs+cues per step)" % (2 * 4 * M * N * B / 1e6),
+                       "parallelism": "dp%d (images shard, no data-path collective)" % world},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "kernels": kernels, "cpu_baseline": cpu_baseline,
+        }))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dsrg321", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

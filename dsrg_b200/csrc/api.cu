@@ -78,6 +78,14 @@ static int lattice_alloc(Engine *e, Lattice &L, int d, int shared) {
     rc |= dalloc(e, &L.vcount, n);
     rc |= dalloc(e, &L.rowbase, (size_t)e->maxB + 1);
     rc |= dalloc(e, &L.nbr, (size_t)(d + 1) * L.nbr_stride);
+    L.maxloc = (d == 2) ? kMaxLocSp : kMaxLocBi;
+    const size_t nt = n * e->ntiles;
+    rc |= dalloc(e, &L.tl_nloc, nt);
+    rc |= dalloc(e, &L.tl_rows, nt * L.maxloc);
+    rc |= dalloc(e, &L.tl_ptr, nt * (L.maxloc + 1));
+    rc |= dalloc(e, &L.tl_ent, nt * 256 * (d + 1));
+    rc |= dalloc(e, &L.tl_loc, n * (d + 1) * L.N);
+    rc |= dalloc(e, &L.wn, n * (d + 1) * L.N);
     if (rc) return DSRG_E_NOMEM;
     if (cudaMemset(L.hkeys, 0xFF, sizeof(uint64_t) * n * L.cap) != cudaSuccess) return DSRG_E_CUDA;
     return DSRG_OK;
@@ -93,6 +101,12 @@ static void lattice_free(Lattice &L) {
     cudaFree(L.vcount);
     cudaFree(L.rowbase);
     cudaFree(L.nbr);
+    cudaFree(L.tl_nloc);
+    cudaFree(L.tl_rows);
+    cudaFree(L.tl_ptr);
+    cudaFree(L.tl_ent);
+    cudaFree(L.tl_loc);
+    cudaFree(L.wn);
 }
 
 static int check_device_flag(Engine *e, cudaStream_t s) {
@@ -258,6 +272,9 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     e->MP = (M + 3) / 4 * 4;
     e->N = H * W;
     e->sm_count = prop.multiProcessorCount;
+    e->tiles_x = (W + kTileW - 1) / kTileW;
+    e->tiles_y = (H + kTileH - 1) / kTileH;
+    e->ntiles = e->tiles_x * e->tiles_y;
     int rc = 0;
     rc |= lattice_alloc(e, e->sp, 2, 1);
     rc |= lattice_alloc(e, e->bi, 5, 0);
@@ -269,6 +286,8 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     rc |= dalloc(e, &e->Q1, n);
     rc |= dalloc(e, &e->spA, (size_t)e->sp.rows_cap * e->MP);
     rc |= dalloc(e, &e->spB, (size_t)e->sp.rows_cap * e->MP);
+    rc |= dalloc(e, &e->spC, (size_t)e->sp.rows_cap * e->MP);
+    rc |= dalloc(e, &e->biC, (size_t)e->bi.rows_cap * e->MP);
     rc |= dalloc(e, &e->biA, (size_t)e->bi.rows_cap * e->MP);
     rc |= dalloc(e, &e->biB, (size_t)e->bi.rows_cap * e->MP);
     rc |= dalloc(e, &e->nvA, (size_t)e->bi.rows_cap);
@@ -297,7 +316,7 @@ void dsrg_engine_destroy(dsrg_engine *h) {
     cudaDeviceSynchronize();
     lattice_free(e->sp);
     lattice_free(e->bi);
-    void *ptrs[] = {e->U, e->Q0, e->Q1, e->spA, e->spB, e->biA, e->biB, e->nvA, e->nvB, e->lmap,
+    void *ptrs[] = {e->U, e->Q0, e->Q1, e->spA, e->spB, e->spC, e->biA, e->biB, e->biC, e->nvA, e->nvB, e->lmap,
                     e->lflag, e->parent, e->hc, e->loss_acc, e->dev_err, e->st_unary, e->st_out,
                     e->st_cues, e->st_labels, e->st_image, e->st_lmap};
     for (void *p : ptrs) cudaFree(p);
@@ -321,8 +340,8 @@ long long dsrg_engine_take_launch_count(dsrg_engine *h) {
 }
 
 static const char *kTagNames[T_COUNT] = {
-    "lattice_insert", "lattice_misc", "lattice_norm", "mf_init", "mf_zero", "mf_splat", "mf_blur_spatial",
-    "mf_blur_bilateral", "mf_slice_update", "mf_export", "srg_label", "srg_merge", "srg_flag", "srg_emit",
+    "lattice_insert", "lattice_misc", "lattice_norm", "mf_init", "mf_zero", "mf_blur_spatial",
+    "mf_blur_bilateral", "mf_tile", "mf_export", "srg_label", "srg_merge", "srg_flag", "srg_emit",
     "seedloss"};
 
 int dsrg_profile_tag_count(void) { return T_COUNT; }

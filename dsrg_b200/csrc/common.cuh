@@ -52,6 +52,15 @@ struct Lattice {
     int32_t *rowbase = nullptr; // [max_batch+1]
     int2 *nbr = nullptr;        // [d+1][rows] (n1,n2): global rows (per-image) or local rows (shared)
     long long nbr_stride = 0;   // rows per axis in nbr
+    // tile-local view (32x8-pixel tiles): the distinct vertices a tile touches, so that splat and
+    // slice run out of shared memory (see tiles.cu)
+    int maxloc = 0;                // local-vertex capacity per tile; tiles beyond it use the fallback
+    int32_t *tl_nloc = nullptr;    // [nimg][ntiles] distinct vertices of the tile, -1 = overflow
+    int32_t *tl_rows = nullptr;    // [nimg][ntiles][maxloc] local row ids (1-based) of those vertices
+    uint16_t *tl_ptr = nullptr;    // [nimg][ntiles][maxloc+1] CSR offsets: entries grouped by local vertex
+    uint16_t *tl_ent = nullptr;    // [nimg][ntiles][256*(d+1)] entries (pixel_in_tile << 3 | r)
+    uint16_t *tl_loc = nullptr;    // [nimg][d+1][N] local vertex index of (pixel, r)
+    float *wn = nullptr;           // [nimg][d+1][N] barycentric weight * norm
     float scale[5] = {0, 0, 0, 0, 0};  // elevation scale factors (permutohedral.cpp:179-182)
     float sigma[5] = {0, 0, 0, 0, 0};  // feature sigmas: x, y[, c0, c1, c2]
 };
@@ -60,13 +69,17 @@ struct Engine;
 
 // kernel classes for the optional per-kernel CUDA-event timing (bench.py's roofline leg)
 enum KTag {
-    T_LAT_INSERT = 0, T_LAT_MISC, T_LAT_NORM, T_MF_INIT, T_MF_ZERO, T_MF_SPLAT, T_MF_BLUR_SP,
-    T_MF_BLUR_BI, T_MF_SLICE, T_MF_EXPORT, T_SRG_LABEL, T_SRG_MERGE, T_SRG_FLAG, T_SRG_EMIT,
+    T_LAT_INSERT = 0, T_LAT_MISC, T_LAT_NORM, T_MF_INIT, T_MF_ZERO, T_MF_BLUR_SP,
+    T_MF_BLUR_BI, T_MF_TILE, T_MF_EXPORT, T_SRG_LABEL, T_SRG_MERGE, T_SRG_FLAG, T_SRG_EMIT,
     T_LOSS, T_COUNT
 };
 
 // ---- lattice.cu ----
 int lattice_build(Engine *e, Lattice &L, int B, const uint8_t *image_dev, cudaStream_t s);
+// ---- tiles.cu ----
+constexpr int kTileW = 32, kTileH = 8;       // one thread per pixel, one warp per tile row
+constexpr int kMaxLocSp = 128, kMaxLocBi = 256;
+int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s);
 // ---- meanfield.cu ----
 int meanfield_run(Engine *e, int B, const float *unary, int unary_layout, bool clamp_inplace,
                   float *unary_rw, const dsrg_crf_params &p, cudaStream_t s);
@@ -97,7 +110,8 @@ struct Engine {
     float *U = nullptr, *Q0 = nullptr, *Q1 = nullptr;
     float *Qcur = nullptr;  // where the current marginals live (Q0 or Q1)
     // lattice value buffers [rows][MP]
-    float *spA = nullptr, *spB = nullptr, *biA = nullptr, *biB = nullptr;
+    float *spA = nullptr, *spB = nullptr, *spC = nullptr, *biA = nullptr, *biB = nullptr, *biC = nullptr;
+    int tiles_x = 0, tiles_y = 0, ntiles = 0;  // 32x8-pixel tiles
     // 1-channel buffers for the normalisation pass
     float *nvA = nullptr, *nvB = nullptr;
     // SRG state

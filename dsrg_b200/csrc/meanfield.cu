@@ -46,53 +46,249 @@ k_mf_init(const float *unary, float *unary_rw, int layout, int clamp, float *U, 
             u[k] = expf(u[k] - mx);
             s += u[k];
         }
+    if (Q) {
 #pragma unroll
-    for (int k = 0; k < MP; k++)
-        if (k < M) Q[((size_t)b * M + k) * N + i] = u[k] / s;
+        for (int k = 0; k < MP; k++)
+            if (k < M) Q[((size_t)b * M + k) * N + i] = u[k] / s;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// splat: values[row] += bary * (Q * norm) for both lattices (pairwise.cpp:66, permutohedral.cpp
-// :545-553).  One thread per pixel, scattered float atomics (first correct version).
+// The fused per-iteration kernel: one CTA per 32x8-pixel tile, one thread per pixel.
+//
+//   slice  : out_i = sum_r (bary_r alpha) values[row_r]            (permutohedral.cpp:574-584)
+//   update : t = U + w2 norm_sp out_sp + w1 norm_bi out_bi ; Q = softmax(t)
+//            (pairwise.cpp:79, labelcompatibility.cpp:46-48, densecrf.cpp:123-128, :98-106)
+//   splat  : values'[row_r] += bary_r (Q_i norm_i)                  (pairwise.cpp:66, permutohedral.cpp:545-553)
+//
+// Fusing the slice of iteration t with the splat of iteration t+1 means Q never goes to HBM
+// between iterations: per iteration the kernel streams U once (4*M*N bytes per image) plus the
+// tile-local lattice view.  The rows a tile touches are staged in shared memory once (slice), the
+// new marginals are parked in shared memory, and the splat walks the tile's CSR (entries grouped
+// by local vertex) so that each distinct vertex receives ONE vectorised global reduction
+// (REDG.ADD.F32x4) per tile instead of one scalar atomic per pixel, vertex and label.
+// norm is folded into the weights (wn = bary*norm, built in tiles.cu).
+// Tiles that touch more distinct vertices than fit (noise images) take the direct global path.
 // ---------------------------------------------------------------------------------------------
-struct LatView {
-    const int32_t *off;   // [nimg][dp1][N]
-    const float *bary;    // [nimg][dp1][N]
-    const float *norm;    // [nimg][N]
-    const int32_t *rowbase;
-    float *val;           // values being splatted into / sliced from
-    int dp1;
+struct TileLat {
+    // direct (fallback) view
+    const int32_t *off;      // [nimg][dp1][N] local row (1-based)
+    const int32_t *rowbase;  // [B+1]
+    // tile-local view
+    const int32_t *tl_nloc;
+    const int32_t *tl_rows;
+    const uint16_t *tl_ptr;
+    const uint16_t *tl_ent;
+    const uint16_t *tl_loc;
+    const float *wn;         // [nimg][dp1][N]
+    const float *val_in;     // blurred values of the previous splat (slice source)
+    float *val_out;          // zeroed values (splat target)
     int shared;
 };
 
-template <int MP>
-__device__ __forceinline__ void splat_one(const LatView &L, int b, int i, int N, int M,
-                                          const float *q) {
-    const int sb = L.shared ? 0 : b;
-    const float nrm = L.norm[(size_t)sb * N + i];
+enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2 };
+
+template <int MP, int DP1, int MAXLOC>
+__device__ __forceinline__ void tile_stage_rows(const TileLat &L, int sb, int b, int tile, int ntiles,
+                                                int nloc, float4 *vs, int *rows_s, bool want_vals) {
+    constexpr int CH = MP / 4;
     const int base = L.rowbase[b];
-    for (int r = 0; r < L.dp1; r++) {
-        size_t at = ((size_t)sb * L.dp1 + r) * N + i;
-        float *row = L.val + (size_t)(base + L.off[at]) * MP;
-        const float w = L.bary[at];
+    const int32_t *rows = L.tl_rows + ((size_t)sb * ntiles + tile) * MAXLOC;
+    for (int i = threadIdx.x; i < nloc; i += 256) rows_s[i] = base + rows[i];
+    if (want_vals) {
+        const float4 *vin = reinterpret_cast<const float4 *>(L.val_in);
+        for (int i = threadIdx.x; i < nloc * CH; i += 256) {
+            const int lv = i / CH, c = i - lv * CH;
+            vs[i] = vin[(size_t)(base + rows[lv]) * CH + c];
+        }
+    }
+}
+
+template <int MP, int DP1>
+__device__ __forceinline__ void tile_slice(const TileLat &L, int sb, int b, int pix, int N, bool fb,
+                                           const float4 *vs, const float *wn_s, float coef, float *t) {
+    constexpr int CH = MP / 4;
+    float acc[MP];
 #pragma unroll
-        for (int k = 0; k < MP; k++)
-            if (k < M) atomicAdd(row + k, __fmul_rn(w, __fmul_rn(q[k], nrm)));
+    for (int k = 0; k < MP; k++) acc[k] = 0.0f;
+    const int base = L.rowbase[b];
+#pragma unroll
+    for (int r = 0; r < DP1; r++) {
+        const size_t at = ((size_t)sb * DP1 + r) * N + pix;
+        const float w = wn_s[r * 256 + threadIdx.x];
+        const float4 *row = fb ? reinterpret_cast<const float4 *>(L.val_in) + (size_t)(base + L.off[at]) * CH
+                               : vs + (size_t)L.tl_loc[at] * CH;
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const float4 v = row[c];
+            acc[4 * c + 0] += w * v.x;
+            acc[4 * c + 1] += w * v.y;
+            acc[4 * c + 2] += w * v.z;
+            acc[4 * c + 3] += w * v.w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < MP; k++) t[k] += coef * acc[k];
+}
+
+// CSR splat of one lattice: warp per local vertex, lane = (entry slot 0..3, label quad 0..MP/4-1)
+template <int MP, int DP1, int MAXLOC>
+__device__ __forceinline__ void tile_splat_csr(const TileLat &L, int nloc, const uint16_t *ptr_s,
+                                               const uint16_t *ent_s, const int *rows_s,
+                                               const float *wn_s, const float4 *qs) {
+    constexpr int CH = MP / 4;
+    static_assert(4 * CH <= 32, "lane mapping");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int es = lane / CH, cq = lane - es * CH;
+    const bool act = es < 4;
+    float4 *vout = reinterpret_cast<float4 *>(L.val_out);
+    for (int lv = warp; lv < nloc; lv += 8) {
+        const int beg = ptr_s[lv], end = ptr_s[lv + 1];
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+            for (int e = beg + es; e < end; e += 4) {
+                const int en = ent_s[e];
+                const int p = en >> 3, r = en & 7;
+                const float w = wn_s[r * 256 + p];
+                const float4 q = qs[p * CH + cq];
+                a.x += w * q.x;
+                a.y += w * q.y;
+                a.z += w * q.z;
+                a.w += w * q.w;
+            }
+        }
+        // fold the 4 entry slots: lanes cq, cq+CH, cq+2CH, cq+3CH
+        a.x += __shfl_down_sync(0xffffffffu, a.x, 2 * CH);
+        a.y += __shfl_down_sync(0xffffffffu, a.y, 2 * CH);
+        a.z += __shfl_down_sync(0xffffffffu, a.z, 2 * CH);
+        a.w += __shfl_down_sync(0xffffffffu, a.w, 2 * CH);
+        a.x += __shfl_down_sync(0xffffffffu, a.x, CH);
+        a.y += __shfl_down_sync(0xffffffffu, a.y, CH);
+        a.z += __shfl_down_sync(0xffffffffu, a.z, CH);
+        a.w += __shfl_down_sync(0xffffffffu, a.w, CH);
+        if (lane < CH) atomicAdd(vout + (size_t)rows_s[lv] * CH + cq, a);
+    }
+}
+
+// direct splat of one pixel (fallback tiles): d+1 rows x MP/4 vector reductions
+template <int MP, int DP1>
+__device__ __forceinline__ void tile_splat_direct(const TileLat &L, int sb, int b, int pix, int N,
+                                                  const float *wn_s, const float *q) {
+    constexpr int CH = MP / 4;
+    const int base = L.rowbase[b];
+    float4 *vout = reinterpret_cast<float4 *>(L.val_out);
+#pragma unroll
+    for (int r = 0; r < DP1; r++) {
+        const size_t at = ((size_t)sb * DP1 + r) * N + pix;
+        const float w = wn_s[r * 256 + threadIdx.x];
+        float4 *row = vout + (size_t)(base + L.off[at]) * CH;
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+            atomicAdd(row + c, make_float4(w * q[4 * c], w * q[4 * c + 1], w * q[4 * c + 2], w * q[4 * c + 3]));
     }
 }
 
 template <int MP>
-__global__ void __launch_bounds__(kThreads)
-k_mf_splat(const float *Q, LatView sp, LatView bi, int M, int N) {
-    const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    float q[MP];
+struct TileSmem {
+    static constexpr int CH = MP / 4;
+    static constexpr int kRows = kMaxLocSp + kMaxLocBi;
+    static constexpr int kBufF4 = (kRows * CH > 256 * CH) ? kRows * CH : 256 * CH;  // vs / qs alias
+    float4 buf[kBufF4];
+    float wn[9 * 256];
+    int rows[kRows];
+    uint16_t ent[9 * 256];
+    uint16_t ptr[kRows + 2];
+};
+
+template <int MP, int MODE>
+__global__ void __launch_bounds__(256, 2)
+k_mf_tile(const float *U, float *Qout, TileLat sp, TileLat bi, float c_sp, float c_bi, int M, int N,
+          int W, int H, int tiles_x, int ntiles) {
+    constexpr int CH = MP / 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<MP> &sm = *reinterpret_cast<TileSmem<MP> *>(smem_raw);
+    const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const int x = tx * kTileW + (tid & 31), y = ty * kTileH + (tid >> 5);
+    const bool in = x < W && y < H;
+    const int pix = in ? y * W + x : 0;
+    const int sb_sp = sp.shared ? 0 : b, sb_bi = bi.shared ? 0 : b;
+    const int nl_sp = sp.tl_nloc[(size_t)sb_sp * ntiles + tile];
+    const int nl_bi = bi.tl_nloc[(size_t)sb_bi * ntiles + tile];
+    const bool fb_sp = nl_sp < 0, fb_bi = nl_bi < 0;
+    const int n_sp = fb_sp ? 0 : nl_sp, n_bi = fb_bi ? 0 : nl_bi;
+    float4 *vs_sp = sm.buf, *vs_bi = sm.buf + kMaxLocSp * CH;
+    int *rows_sp = sm.rows, *rows_bi = sm.rows + kMaxLocSp;
+
+    // stage: weights (thread = pixel), the rows this tile touches, and the CSR for the splat
+    float t[MP];
+#pragma unroll
+    for (int k = 0; k < MP; k++) t[k] = (in && k < M) ? U[((size_t)b * M + k) * N + pix] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; r++) sm.wn[r * 256 + tid] = in ? sp.wn[((size_t)sb_sp * 3 + r) * N + pix] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < 6; r++) sm.wn[(3 + r) * 256 + tid] = in ? bi.wn[((size_t)sb_bi * 6 + r) * N + pix] : 0.0f;
+    tile_stage_rows<MP, 3, kMaxLocSp>(sp, sb_sp, b, tile, ntiles, n_sp, vs_sp, rows_sp, MODE != MODE_FIRST);
+    tile_stage_rows<MP, 6, kMaxLocBi>(bi, sb_bi, b, tile, ntiles, n_bi, vs_bi, rows_bi, MODE != MODE_FIRST);
+    if (MODE != MODE_LAST) {
+        const uint16_t *e_sp = sp.tl_ent + ((size_t)sb_sp * ntiles + tile) * (256 * 3);
+        const uint16_t *e_bi = bi.tl_ent + ((size_t)sb_bi * ntiles + tile) * (256 * 6);
+        const uint16_t *p_sp = sp.tl_ptr + ((size_t)sb_sp * ntiles + tile) * (kMaxLocSp + 1);
+        const uint16_t *p_bi = bi.tl_ptr + ((size_t)sb_bi * ntiles + tile) * (kMaxLocBi + 1);
+        if (!fb_sp) {
+            const int ne = p_sp[n_sp];
+            for (int i = tid; i < ne; i += 256) sm.ent[i] = e_sp[i];
+            for (int i = tid; i <= n_sp; i += 256) sm.ptr[i] = p_sp[i];
+        }
+        if (!fb_bi) {
+            const int ne = p_bi[n_bi];
+            for (int i = tid; i < ne; i += 256) sm.ent[3 * 256 + i] = e_bi[i];
+            for (int i = tid; i <= n_bi; i += 256) sm.ptr[kMaxLocSp + 1 + i] = p_bi[i];
+        }
+    }
+    __syncthreads();
+
+    if (MODE != MODE_FIRST) {
+        if (in) {
+            tile_slice<MP, 3>(sp, sb_sp, b, pix, N, fb_sp, vs_sp, sm.wn, c_sp, t);
+            tile_slice<MP, 6>(bi, sb_bi, b, pix, N, fb_bi, vs_bi, sm.wn + 3 * 256, c_bi, t);
+        }
+    }
+    // Q = softmax(t)  (expAndNormalize, densecrf.cpp:98-106)
+    float mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < MP; k++)
-        if (k < M) q[k] = Q[((size_t)b * M + k) * N + i];
-    splat_one<MP>(sp, b, i, N, M, q);
-    splat_one<MP>(bi, b, i, N, M, q);
+        if (k < M) mx = fmaxf(mx, t[k]);
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < MP; k++) {
+        t[k] = (k < M) ? expf(t[k] - mx) : 0.0f;
+        s += t[k];
+    }
+#pragma unroll
+    for (int k = 0; k < MP; k++) t[k] = (k < M) ? t[k] / s : 0.0f;
+    if (MODE == MODE_LAST) {
+        if (in) {
+#pragma unroll
+            for (int k = 0; k < MP; k++)
+                if (k < M) Qout[((size_t)b * M + k) * N + pix] = t[k];
+        }
+        return;
+    }
+    __syncthreads();  // every thread is done reading the staged rows: reuse the buffer for Q
+    float4 *qs = sm.buf;
+#pragma unroll
+    for (int c = 0; c < CH; c++) qs[tid * CH + c] = make_float4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+    __syncthreads();
+    if (!fb_sp)
+        tile_splat_csr<MP, 3, kMaxLocSp>(sp, n_sp, sm.ptr, sm.ent, rows_sp, sm.wn, qs);
+    else if (in)
+        tile_splat_direct<MP, 3>(sp, sb_sp, b, pix, N, sm.wn, t);
+    if (!fb_bi)
+        tile_splat_csr<MP, 6, kMaxLocBi>(bi, n_bi, sm.ptr + kMaxLocSp + 1, sm.ent + 3 * 256, rows_bi,
+                                         sm.wn + 3 * 256, qs);
+    else if (in)
+        tile_splat_direct<MP, 6>(bi, sb_bi, b, pix, N, sm.wn + 3 * 256, t);
 }
 
 // zero the splat targets of both lattices (row counts are device-resident)
@@ -142,72 +338,6 @@ k_mf_blur(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase
         r.w = o.w + 0.5f * (a.w + d.w);
         out[g * CH + c] = r;
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// slice both lattices, apply norm + Potts, add to the unary and renormalise:
-//   t = U + w2 * norm_sp * slice_sp + w1 * norm_bi * slice_bi ;  Q = softmax(t)
-// (permutohedral.cpp:574-584, pairwise.cpp:79, labelcompatibility.cpp:46-48,
-//  densecrf.cpp:123-128: tmp1 = -unary; tmp1 -= (-w * K Q) for the Gaussian, then the bilateral).
-// ---------------------------------------------------------------------------------------------
-template <int MP>
-__device__ __forceinline__ void slice_one(const LatView &L, int b, int i, int N, float alpha,
-                                          float *acc) {
-    const int sb = L.shared ? 0 : b;
-    const int base = L.rowbase[b];
-#pragma unroll
-    for (int k = 0; k < MP; k++) acc[k] = 0.0f;
-    for (int r = 0; r < L.dp1; r++) {
-        size_t at = ((size_t)sb * L.dp1 + r) * N + i;
-        const float4 *row = reinterpret_cast<const float4 *>(L.val + (size_t)(base + L.off[at]) * MP);
-        const float w = __fmul_rn(L.bary[at], alpha);  // bary * alpha (:579)
-#pragma unroll
-        for (int c = 0; c < MP / 4; c++) {
-            float4 v = row[c];
-            acc[4 * c + 0] += w * v.x;
-            acc[4 * c + 1] += w * v.y;
-            acc[4 * c + 2] += w * v.z;
-            acc[4 * c + 3] += w * v.w;
-        }
-    }
-}
-
-template <int MP>
-__global__ void __launch_bounds__(kThreads)
-k_mf_slice_update(const float *U, float *Qout, LatView sp, LatView bi, float w_sp, float w_bi,
-                  float alpha_sp, float alpha_bi, int M, int N) {
-    const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    float t[MP], acc[MP];
-#pragma unroll
-    for (int k = 0; k < MP; k++) t[k] = (k < M) ? U[((size_t)b * M + k) * N + i] : 0.0f;
-    {
-        slice_one<MP>(sp, b, i, N, alpha_sp, acc);
-        const float nrm = sp.norm[i];
-#pragma unroll
-        for (int k = 0; k < MP; k++) t[k] += w_sp * (acc[k] * nrm);
-    }
-    {
-        slice_one<MP>(bi, b, i, N, alpha_bi, acc);
-        const float nrm = bi.norm[(size_t)b * N + i];
-#pragma unroll
-        for (int k = 0; k < MP; k++) t[k] += w_bi * (acc[k] * nrm);
-    }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < MP; k++)
-        if (k < M) mx = fmaxf(mx, t[k]);
-    float s = 0.0f;
-#pragma unroll
-    for (int k = 0; k < MP; k++)
-        if (k < M) {
-            t[k] = expf(t[k] - mx);
-            s += t[k];
-        }
-#pragma unroll
-    for (int k = 0; k < MP; k++)
-        if (k < M) Qout[((size_t)b * M + k) * N + i] = t[k] / s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,16 +397,38 @@ k_mf_export_renorm(const float *Q, float *result_out, float *log_out, int M, int
     }
 }
 
-static LatView make_view(const Lattice &L, float *val) {
-    LatView v;
+static TileLat make_tile_view(const Lattice &L, const float *val_in, float *val_out) {
+    TileLat v;
     v.off = L.off;
-    v.bary = L.bary;
-    v.norm = L.norm;
     v.rowbase = L.rowbase;
-    v.val = val;
-    v.dp1 = L.d + 1;
+    v.tl_nloc = L.tl_nloc;
+    v.tl_rows = L.tl_rows;
+    v.tl_ptr = L.tl_ptr;
+    v.tl_ent = L.tl_ent;
+    v.tl_loc = L.tl_loc;
+    v.wn = L.wn;
+    v.val_in = val_in;
+    v.val_out = val_out;
     v.shared = L.shared;
     return v;
+}
+
+// blur `buf` (just splatted) along all d+1 axes, ping-ponging with `tmp`; returns where the
+// result lives
+template <int MP>
+static float *blur_all(Engine *e, const Lattice &L, float *buf, float *tmp, int B, int tag, cudaStream_t s) {
+    float *src = buf, *dst = tmp;
+    const int grid = 8 * e->sm_count;
+    for (int j = 0; j <= L.d; j++) {
+        DSRG_LAUNCH(e, tag, s,
+                    k_mf_blur<MP><<<grid, kThreads, 0, s>>>((const float4 *)src, (float4 *)dst,
+                                                            L.nbr + (size_t)j * L.nbr_stride, L.rowbase, B,
+                                                            L.shared));
+        float *t = src;
+        src = dst;
+        dst = t;
+    }
+    return src;
 }
 
 template <int MP>
@@ -284,43 +436,57 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
                     const dsrg_crf_params &p, cudaStream_t s) {
     const int M = e->M, N = e->N;
     dim3 gp(cdiv(N, kThreads), B);
-    DSRG_LAUNCH(e, T_MF_INIT, s, k_mf_init<MP><<<gp, kThreads, 0, s>>>(unary, unary_rw, layout, clamp ? 1 : 0, e->U, e->Q0, M, N));
-    float *Qc = e->Q0, *Qn = e->Q1;
+    const int T = p.n_iters;
+    DSRG_LAUNCH(e, T_MF_INIT, s,
+                k_mf_init<MP><<<gp, kThreads, 0, s>>>(unary, unary_rw, layout, clamp ? 1 : 0, e->U,
+                                                      T == 0 ? e->Q0 : nullptr, M, N));
+    e->Qcur = e->Q0;
+    if (T == 0) return DSRG_OK;
     const float alpha_sp = 1.0f / (1 + powf(2, -e->sp.d));  // permutohedral.cpp:571
     const float alpha_bi = 1.0f / (1 + powf(2, -e->bi.d));
-    const int blur_grid = 8 * e->sm_count;
-    for (int it = 0; it < p.n_iters; it++) {
-        // the row counts live on the device only (no host sync on the path)
-        DSRG_LAUNCH(e, T_MF_ZERO, s,
-                    k_mf_zero<MP><<<blur_grid, kThreads, 0, s>>>((float4 *)e->spA, e->sp.rowbase, (float4 *)e->biA,
-                                                                 e->bi.rowbase, B));
-        DSRG_LAUNCH(e, T_MF_SPLAT, s,
-                    k_mf_splat<MP><<<gp, kThreads, 0, s>>>(Qc, make_view(e->sp, e->spA), make_view(e->bi, e->biA), M, N));
-        float *src = e->spA, *dst = e->spB;
-        for (int j = 0; j <= e->sp.d; j++) {
-            DSRG_LAUNCH(e, T_MF_BLUR_SP, s,
-                        k_mf_blur<MP><<<blur_grid, kThreads, 0, s>>>((const float4 *)src, (float4 *)dst,
-                                                                     e->sp.nbr + (size_t)j * e->sp.nbr_stride,
-                                                                     e->sp.rowbase, B, 1));
-            float *t = src; src = dst; dst = t;
-        }
-        float *sp_final = src;
-        src = e->biA; dst = e->biB;
-        for (int j = 0; j <= e->bi.d; j++) {
-            DSRG_LAUNCH(e, T_MF_BLUR_BI, s,
-                        k_mf_blur<MP><<<blur_grid, kThreads, 0, s>>>((const float4 *)src, (float4 *)dst,
-                                                                     e->bi.nbr + (size_t)j * e->bi.nbr_stride,
-                                                                     e->bi.rowbase, B, 0));
-            float *t = src; src = dst; dst = t;
-        }
-        float *bi_final = src;
-        DSRG_LAUNCH(e, T_MF_SLICE, s,
-                    k_mf_slice_update<MP><<<gp, kThreads, 0, s>>>(e->U, Qn, make_view(e->sp, sp_final),
-                                                                  make_view(e->bi, bi_final), p.w2, p.w1,
-                                                                  alpha_sp, alpha_bi, M, N));
-        float *t = Qc; Qc = Qn; Qn = t;
+    const float c_sp = p.w2 * alpha_sp, c_bi = p.w1 * alpha_bi;
+    const size_t smem = sizeof(TileSmem<MP>);
+    static bool attr_done[3] = {false, false, false};
+    if (!attr_done[0]) {
+        DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[0] = true;
     }
-    e->Qcur = Qc;
+    dim3 gt(e->ntiles, B);
+    const int zgrid = 8 * e->sm_count;
+    // three value buffers per lattice: X = blurred values being sliced, Y = zeroed splat target,
+    // Z = blur scratch
+    float *spX = e->spA, *spY = e->spB, *spZ = e->spC;
+    float *biX = e->biA, *biY = e->biB, *biZ = e->biC;
+    DSRG_LAUNCH(e, T_MF_ZERO, s,
+                k_mf_zero<MP><<<zgrid, kThreads, 0, s>>>((float4 *)spY, e->sp.rowbase, (float4 *)biY, e->bi.rowbase, B));
+    for (int it = 0; it <= T; it++) {
+        TileLat vsp = make_tile_view(e->sp, spX, spY), vbi = make_tile_view(e->bi, biX, biY);
+        if (it == 0) {
+            DSRG_LAUNCH(e, T_MF_TILE, s,
+                        (k_mf_tile<MP, MODE_FIRST><<<gt, 256, smem, s>>>(e->U, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
+                                                                         e->H, e->tiles_x, e->ntiles)));
+        } else if (it < T) {
+            DSRG_LAUNCH(e, T_MF_TILE, s,
+                        (k_mf_tile<MP, MODE_MID><<<gt, 256, smem, s>>>(e->U, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
+                                                                       e->H, e->tiles_x, e->ntiles)));
+        } else {
+            DSRG_LAUNCH(e, T_MF_TILE, s,
+                        (k_mf_tile<MP, MODE_LAST><<<gt, 256, smem, s>>>(e->U, e->Q0, vsp, vbi, c_sp, c_bi, M, N, e->W,
+                                                                        e->H, e->tiles_x, e->ntiles)));
+            break;
+        }
+        // the old X is dead: it becomes the next (zeroed) splat target
+        DSRG_LAUNCH(e, T_MF_ZERO, s,
+                    k_mf_zero<MP><<<zgrid, kThreads, 0, s>>>((float4 *)spX, e->sp.rowbase, (float4 *)biX, e->bi.rowbase, B));
+        float *sp_res = blur_all<MP>(e, e->sp, spY, spZ, B, T_MF_BLUR_SP, s);
+        float *bi_res = blur_all<MP>(e, e->bi, biY, biZ, B, T_MF_BLUR_BI, s);
+        float *sp_other = (sp_res == spY) ? spZ : spY, *bi_other = (bi_res == biY) ? biZ : biY;
+        float *nspY = spX, *nbiY = biX;
+        spX = sp_res; spY = nspY; spZ = sp_other;
+        biX = bi_res; biY = nbiY; biZ = bi_other;
+    }
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }
