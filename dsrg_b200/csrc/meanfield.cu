@@ -88,73 +88,94 @@ struct TileLat {
 
 enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2 };
 
-template <int MP, int DP1, int MAXLOC>
-__device__ __forceinline__ void tile_stage_rows(const TileLat &L, int sb, int b, int tile, int ntiles,
-                                                int nloc, float4 *vs, int *rows_s, bool want_vals) {
-    constexpr int CH = MP / 4;
-    const int base = L.rowbase[b];
-    const int32_t *rows = L.tl_rows + ((size_t)sb * ntiles + tile) * MAXLOC;
-    for (int i = threadIdx.x; i < nloc; i += 256) rows_s[i] = base + rows[i];
-    if (want_vals) {
-        const float4 *vin = reinterpret_cast<const float4 *>(L.val_in);
-        for (int i = threadIdx.x; i < nloc * CH; i += 256) {
-            const int lv = i / CH, c = i - lv * CH;
-            vs[i] = vin[(size_t)(base + rows[lv]) * CH + c];
-        }
-    }
+// exp(x) for x <= 0 via ex2.approx with the rounding error of x*log2(e) folded back in
+// (relative error ~2^-22, independent of |x|)
+__device__ __forceinline__ float exp_neg(float x) {
+    const float kL2E = 1.4426950408889634f, kL2E_lo = 1.9259630e-8f, kLn2 = 0.6931471805599453f;
+    const float t = x * kL2E;
+    float r = fmaf(x, kL2E, -t);
+    r = fmaf(x, kL2E_lo, r);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return fmaf(e, r * kLn2, e);
 }
 
+template <int MP>
+struct TileSmem {
+    static constexpr int CH = MP / 4;
+    static constexpr int kRows = kMaxLocSp + kMaxLocBi;
+    static constexpr int kBufF4 = (kRows * CH > 256 * CH) ? kRows * CH : 256 * CH;  // vs / qs alias
+    float4 buf[kBufF4];
+    int2 ent[9 * 256];   // (byte offset of the pixel's Q row, weight bits), CSR order
+    float wn[9 * 256];
+    int rows[kRows];
+    uint16_t ptr[kRows + 2];
+};
+
+// slice one lattice from the staged rows (shared memory): t += coef * sum_r wn_r * row_r
 template <int MP, int DP1>
-__device__ __forceinline__ void tile_slice(const TileLat &L, int sb, int b, int pix, int N, bool fb,
-                                           const float4 *vs, const float *wn_s, float coef, float *t) {
+__device__ __forceinline__ void tile_slice_smem(const float4 *vs, const uint16_t *loc, size_t stride,
+                                                const float *w, float coef, float *t) {
     constexpr int CH = MP / 4;
-    float acc[MP];
-#pragma unroll
-    for (int k = 0; k < MP; k++) acc[k] = 0.0f;
-    const int base = L.rowbase[b];
 #pragma unroll
     for (int r = 0; r < DP1; r++) {
-        const size_t at = ((size_t)sb * DP1 + r) * N + pix;
-        const float w = wn_s[r * 256 + threadIdx.x];
-        const float4 *row = fb ? reinterpret_cast<const float4 *>(L.val_in) + (size_t)(base + L.off[at]) * CH
-                               : vs + (size_t)L.tl_loc[at] * CH;
+        const float4 *row = vs + (int)loc[r * stride] * CH;
+        const float wr = coef * w[r];
 #pragma unroll
         for (int c = 0; c < CH; c++) {
             const float4 v = row[c];
-            acc[4 * c + 0] += w * v.x;
-            acc[4 * c + 1] += w * v.y;
-            acc[4 * c + 2] += w * v.z;
-            acc[4 * c + 3] += w * v.w;
+            t[4 * c + 0] = fmaf(wr, v.x, t[4 * c + 0]);
+            t[4 * c + 1] = fmaf(wr, v.y, t[4 * c + 1]);
+            t[4 * c + 2] = fmaf(wr, v.z, t[4 * c + 2]);
+            t[4 * c + 3] = fmaf(wr, v.w, t[4 * c + 3]);
         }
     }
+}
+
+// fallback: slice straight from the global value rows
+template <int MP, int DP1>
+__device__ __forceinline__ void tile_slice_global(const float4 *vin, const int32_t *off, size_t stride,
+                                                  int base, const float *w, float coef, float *t) {
+    constexpr int CH = MP / 4;
 #pragma unroll
-    for (int k = 0; k < MP; k++) t[k] += coef * acc[k];
+    for (int r = 0; r < DP1; r++) {
+        const float4 *row = vin + (size_t)(base + off[r * stride]) * CH;
+        const float wr = coef * w[r];
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const float4 v = row[c];
+            t[4 * c + 0] = fmaf(wr, v.x, t[4 * c + 0]);
+            t[4 * c + 1] = fmaf(wr, v.y, t[4 * c + 1]);
+            t[4 * c + 2] = fmaf(wr, v.z, t[4 * c + 2]);
+            t[4 * c + 3] = fmaf(wr, v.w, t[4 * c + 3]);
+        }
+    }
 }
 
 // CSR splat of one lattice: warp per local vertex, lane = (entry slot 0..3, label quad 0..MP/4-1)
-template <int MP, int DP1, int MAXLOC>
-__device__ __forceinline__ void tile_splat_csr(const TileLat &L, int nloc, const uint16_t *ptr_s,
-                                               const uint16_t *ent_s, const int *rows_s,
-                                               const float *wn_s, const float4 *qs) {
+template <int MP>
+__device__ __forceinline__ void tile_splat_csr(float4 *vout, int nloc, const uint16_t *ptr_s,
+                                               const int2 *ent_s, const int *rows_s,
+                                               const unsigned char *qs_bytes) {
     constexpr int CH = MP / 4;
     static_assert(4 * CH <= 32, "lane mapping");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int es = lane / CH, cq = lane - es * CH;
     const bool act = es < 4;
-    float4 *vout = reinterpret_cast<float4 *>(L.val_out);
+    const unsigned char *qbase = qs_bytes + cq * 16;
     for (int lv = warp; lv < nloc; lv += 8) {
         const int beg = ptr_s[lv], end = ptr_s[lv + 1];
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
+#pragma unroll 2
             for (int e = beg + es; e < end; e += 4) {
-                const int en = ent_s[e];
-                const int p = en >> 3, r = en & 7;
-                const float w = wn_s[r * 256 + p];
-                const float4 q = qs[p * CH + cq];
-                a.x += w * q.x;
-                a.y += w * q.y;
-                a.z += w * q.z;
-                a.w += w * q.w;
+                const int2 en = ent_s[e];
+                const float w = __int_as_float(en.y);
+                const float4 q = *reinterpret_cast<const float4 *>(qbase + en.x);
+                a.x = fmaf(w, q.x, a.x);
+                a.y = fmaf(w, q.y, a.y);
+                a.z = fmaf(w, q.z, a.z);
+                a.w = fmaf(w, q.w, a.w);
             }
         }
         // fold the 4 entry slots: lanes cq, cq+CH, cq+2CH, cq+3CH
@@ -172,38 +193,23 @@ __device__ __forceinline__ void tile_splat_csr(const TileLat &L, int nloc, const
 
 // direct splat of one pixel (fallback tiles): d+1 rows x MP/4 vector reductions
 template <int MP, int DP1>
-__device__ __forceinline__ void tile_splat_direct(const TileLat &L, int sb, int b, int pix, int N,
-                                                  const float *wn_s, const float *q) {
+__device__ __forceinline__ void tile_splat_direct(float4 *vout, const int32_t *off, size_t stride,
+                                                  int base, const float *w, const float *q) {
     constexpr int CH = MP / 4;
-    const int base = L.rowbase[b];
-    float4 *vout = reinterpret_cast<float4 *>(L.val_out);
 #pragma unroll
     for (int r = 0; r < DP1; r++) {
-        const size_t at = ((size_t)sb * DP1 + r) * N + pix;
-        const float w = wn_s[r * 256 + threadIdx.x];
-        float4 *row = vout + (size_t)(base + L.off[at]) * CH;
+        float4 *row = vout + (size_t)(base + off[r * stride]) * CH;
 #pragma unroll
         for (int c = 0; c < CH; c++)
-            atomicAdd(row + c, make_float4(w * q[4 * c], w * q[4 * c + 1], w * q[4 * c + 2], w * q[4 * c + 3]));
+            atomicAdd(row + c, make_float4(w[r] * q[4 * c], w[r] * q[4 * c + 1], w[r] * q[4 * c + 2],
+                                           w[r] * q[4 * c + 3]));
     }
 }
 
-template <int MP>
-struct TileSmem {
-    static constexpr int CH = MP / 4;
-    static constexpr int kRows = kMaxLocSp + kMaxLocBi;
-    static constexpr int kBufF4 = (kRows * CH > 256 * CH) ? kRows * CH : 256 * CH;  // vs / qs alias
-    float4 buf[kBufF4];
-    float wn[9 * 256];
-    int rows[kRows];
-    uint16_t ent[9 * 256];
-    uint16_t ptr[kRows + 2];
-};
-
 template <int MP, int MODE>
-__global__ void __launch_bounds__(256, 2)
-k_mf_tile(const float *U, float *Qout, TileLat sp, TileLat bi, float c_sp, float c_bi, int M, int N,
-          int W, int H, int tiles_x, int ntiles) {
+__global__ void __launch_bounds__(256, 3)
+k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
+          float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles) {
     constexpr int CH = MP / 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem<MP> &sm = *reinterpret_cast<TileSmem<MP> *>(smem_raw);
@@ -213,46 +219,86 @@ k_mf_tile(const float *U, float *Qout, TileLat sp, TileLat bi, float c_sp, float
     const bool in = x < W && y < H;
     const int pix = in ? y * W + x : 0;
     const int sb_sp = sp.shared ? 0 : b, sb_bi = bi.shared ? 0 : b;
-    const int nl_sp = sp.tl_nloc[(size_t)sb_sp * ntiles + tile];
-    const int nl_bi = bi.tl_nloc[(size_t)sb_bi * ntiles + tile];
+    const size_t ti_sp = (size_t)sb_sp * ntiles + tile, ti_bi = (size_t)sb_bi * ntiles + tile;
+    const int nl_sp = sp.tl_nloc[ti_sp], nl_bi = bi.tl_nloc[ti_bi];
     const bool fb_sp = nl_sp < 0, fb_bi = nl_bi < 0;
     const int n_sp = fb_sp ? 0 : nl_sp, n_bi = fb_bi ? 0 : nl_bi;
+    const int base_sp = sp.rowbase[b], base_bi = bi.rowbase[b];
     float4 *vs_sp = sm.buf, *vs_bi = sm.buf + kMaxLocSp * CH;
     int *rows_sp = sm.rows, *rows_bi = sm.rows + kMaxLocSp;
+    const size_t strideN = (size_t)N;
+    const size_t px_sp = (size_t)sb_sp * 3 * N + pix, px_bi = (size_t)sb_bi * 6 * N + pix;
 
-    // stage: weights (thread = pixel), the rows this tile touches, and the CSR for the splat
+    // ---- phase A: per-pixel data (thread = pixel) and the tile's row list ----
     float t[MP];
+    {
+        const float *Ub = U + (size_t)b * M * N + pix;
 #pragma unroll
-    for (int k = 0; k < MP; k++) t[k] = (in && k < M) ? U[((size_t)b * M + k) * N + pix] : 0.0f;
+        for (int k = 0; k < MP; k++) t[k] = (in && k < M) ? Ub[(size_t)k * N] : 0.0f;
+    }
+    float w_sp[3], w_bi[6];
 #pragma unroll
-    for (int r = 0; r < 3; r++) sm.wn[r * 256 + tid] = in ? sp.wn[((size_t)sb_sp * 3 + r) * N + pix] : 0.0f;
+    for (int r = 0; r < 3; r++) {
+        w_sp[r] = in ? sp.wn[px_sp + r * strideN] : 0.0f;
+        sm.wn[r * 256 + tid] = w_sp[r];
+    }
 #pragma unroll
-    for (int r = 0; r < 6; r++) sm.wn[(3 + r) * 256 + tid] = in ? bi.wn[((size_t)sb_bi * 6 + r) * N + pix] : 0.0f;
-    tile_stage_rows<MP, 3, kMaxLocSp>(sp, sb_sp, b, tile, ntiles, n_sp, vs_sp, rows_sp, MODE != MODE_FIRST);
-    tile_stage_rows<MP, 6, kMaxLocBi>(bi, sb_bi, b, tile, ntiles, n_bi, vs_bi, rows_bi, MODE != MODE_FIRST);
+    for (int r = 0; r < 6; r++) {
+        w_bi[r] = in ? bi.wn[px_bi + r * strideN] : 0.0f;
+        sm.wn[(3 + r) * 256 + tid] = w_bi[r];
+    }
+    {
+        const int32_t *r_sp = sp.tl_rows + ti_sp * kMaxLocSp, *r_bi = bi.tl_rows + ti_bi * kMaxLocBi;
+        for (int i = tid; i < n_sp; i += 256) rows_sp[i] = base_sp + r_sp[i];
+        for (int i = tid; i < n_bi; i += 256) rows_bi[i] = base_bi + r_bi[i];
+    }
+    const uint16_t *p_sp = sp.tl_ptr + ti_sp * (kMaxLocSp + 1), *p_bi = bi.tl_ptr + ti_bi * (kMaxLocBi + 1);
+    const int ne_sp = (MODE != MODE_LAST && !fb_sp) ? p_sp[n_sp] : 0;
+    const int ne_bi = (MODE != MODE_LAST && !fb_bi) ? p_bi[n_bi] : 0;
+    __syncthreads();
+
+    // ---- phase B: stage the value rows (slice source) and pack the CSR entries (splat) ----
+    if (MODE != MODE_FIRST) {
+        const float4 *vin_sp = reinterpret_cast<const float4 *>(sp.val_in);
+        const float4 *vin_bi = reinterpret_cast<const float4 *>(bi.val_in);
+        for (int i = tid; i < n_sp * CH; i += 256) {
+            const int lv = i / CH, c = i - lv * CH;
+            vs_sp[i] = vin_sp[(size_t)rows_sp[lv] * CH + c];
+        }
+        for (int i = tid; i < n_bi * CH; i += 256) {
+            const int lv = i / CH, c = i - lv * CH;
+            vs_bi[i] = vin_bi[(size_t)rows_bi[lv] * CH + c];
+        }
+    }
     if (MODE != MODE_LAST) {
-        const uint16_t *e_sp = sp.tl_ent + ((size_t)sb_sp * ntiles + tile) * (256 * 3);
-        const uint16_t *e_bi = bi.tl_ent + ((size_t)sb_bi * ntiles + tile) * (256 * 6);
-        const uint16_t *p_sp = sp.tl_ptr + ((size_t)sb_sp * ntiles + tile) * (kMaxLocSp + 1);
-        const uint16_t *p_bi = bi.tl_ptr + ((size_t)sb_bi * ntiles + tile) * (kMaxLocBi + 1);
-        if (!fb_sp) {
-            const int ne = p_sp[n_sp];
-            for (int i = tid; i < ne; i += 256) sm.ent[i] = e_sp[i];
-            for (int i = tid; i <= n_sp; i += 256) sm.ptr[i] = p_sp[i];
+        const uint16_t *e_sp = sp.tl_ent + ti_sp * (256 * 3), *e_bi = bi.tl_ent + ti_bi * (256 * 6);
+        for (int i = tid; i < ne_sp; i += 256) {
+            const int en = e_sp[i];
+            const int p = en >> 3, r = en & 7;
+            sm.ent[i] = make_int2(p * (CH * 16), __float_as_int(sm.wn[r * 256 + p]));
         }
-        if (!fb_bi) {
-            const int ne = p_bi[n_bi];
-            for (int i = tid; i < ne; i += 256) sm.ent[3 * 256 + i] = e_bi[i];
-            for (int i = tid; i <= n_bi; i += 256) sm.ptr[kMaxLocSp + 1 + i] = p_bi[i];
+        for (int i = tid; i < ne_bi; i += 256) {
+            const int en = e_bi[i];
+            const int p = en >> 3, r = en & 7;
+            sm.ent[3 * 256 + i] = make_int2(p * (CH * 16), __float_as_int(sm.wn[(3 + r) * 256 + p]));
         }
+        for (int i = tid; i <= n_sp; i += 256) sm.ptr[i] = p_sp[i];
+        for (int i = tid; i <= n_bi; i += 256) sm.ptr[kMaxLocSp + 1 + i] = p_bi[i];
     }
     __syncthreads();
 
-    if (MODE != MODE_FIRST) {
-        if (in) {
-            tile_slice<MP, 3>(sp, sb_sp, b, pix, N, fb_sp, vs_sp, sm.wn, c_sp, t);
-            tile_slice<MP, 6>(bi, sb_bi, b, pix, N, fb_bi, vs_bi, sm.wn + 3 * 256, c_bi, t);
-        }
+    // ---- slice + update ----
+    if (MODE != MODE_FIRST && in) {
+        if (!fb_sp)
+            tile_slice_smem<MP, 3>(vs_sp, sp.tl_loc + px_sp, strideN, w_sp, c_sp, t);
+        else
+            tile_slice_global<MP, 3>(reinterpret_cast<const float4 *>(sp.val_in), sp.off + px_sp, strideN,
+                                     base_sp, w_sp, c_sp, t);
+        if (!fb_bi)
+            tile_slice_smem<MP, 6>(vs_bi, bi.tl_loc + px_bi, strideN, w_bi, c_bi, t);
+        else
+            tile_slice_global<MP, 6>(reinterpret_cast<const float4 *>(bi.val_in), bi.off + px_bi, strideN,
+                                     base_bi, w_bi, c_bi, t);
     }
     // Q = softmax(t)  (expAndNormalize, densecrf.cpp:98-106)
     float mx = -INFINITY;
@@ -262,16 +308,18 @@ k_mf_tile(const float *U, float *Qout, TileLat sp, TileLat bi, float c_sp, float
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < MP; k++) {
-        t[k] = (k < M) ? expf(t[k] - mx) : 0.0f;
+        t[k] = (k < M) ? exp_neg(t[k] - mx) : 0.0f;
         s += t[k];
     }
+    const float inv = __frcp_rn(s);
 #pragma unroll
-    for (int k = 0; k < MP; k++) t[k] = (k < M) ? t[k] / s : 0.0f;
+    for (int k = 0; k < MP; k++) t[k] *= inv;
     if (MODE == MODE_LAST) {
         if (in) {
+            float *Qb = Qout + (size_t)b * M * N + pix;
 #pragma unroll
             for (int k = 0; k < MP; k++)
-                if (k < M) Qout[((size_t)b * M + k) * N + pix] = t[k];
+                if (k < M) Qb[(size_t)k * N] = t[k];
         }
         return;
     }
@@ -280,15 +328,17 @@ k_mf_tile(const float *U, float *Qout, TileLat sp, TileLat bi, float c_sp, float
 #pragma unroll
     for (int c = 0; c < CH; c++) qs[tid * CH + c] = make_float4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
     __syncthreads();
+    // ---- splat ----
+    float4 *vout_sp = reinterpret_cast<float4 *>(sp.val_out), *vout_bi = reinterpret_cast<float4 *>(bi.val_out);
     if (!fb_sp)
-        tile_splat_csr<MP, 3, kMaxLocSp>(sp, n_sp, sm.ptr, sm.ent, rows_sp, sm.wn, qs);
+        tile_splat_csr<MP>(vout_sp, n_sp, sm.ptr, sm.ent, rows_sp, reinterpret_cast<const unsigned char *>(qs));
     else if (in)
-        tile_splat_direct<MP, 3>(sp, sb_sp, b, pix, N, sm.wn, t);
+        tile_splat_direct<MP, 3>(vout_sp, sp.off + px_sp, strideN, base_sp, w_sp, t);
     if (!fb_bi)
-        tile_splat_csr<MP, 6, kMaxLocBi>(bi, n_bi, sm.ptr + kMaxLocSp + 1, sm.ent + 3 * 256, rows_bi,
-                                         sm.wn + 3 * 256, qs);
+        tile_splat_csr<MP>(vout_bi, n_bi, sm.ptr + kMaxLocSp + 1, sm.ent + 3 * 256, rows_bi,
+                           reinterpret_cast<const unsigned char *>(qs));
     else if (in)
-        tile_splat_direct<MP, 6>(bi, sb_bi, b, pix, N, sm.wn + 3 * 256, t);
+        tile_splat_direct<MP, 6>(vout_bi, bi.off + px_bi, strideN, base_bi, w_bi, t);
 }
 
 // zero the splat targets of both lattices (row counts are device-resident)
