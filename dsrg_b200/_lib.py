@@ -40,6 +40,7 @@ SIGNATURES = {
     "dsrg_engine_create": (_vp, [_i, _i, _i, _i, _i]),
     "dsrg_engine_destroy": (None, [_vp]),
     "dsrg_engine_device_bytes": (_sz, [_vp]),
+    "dsrg_engine_set_host_chunk": (_i, [_vp, _i]),
     "dsrg_engine_take_launch_count": (_ll, [_vp]),
     "dsrg_crf_batch_dev": (_i, [_vp, _i, _vp, _i, _vp, _pp, _vp, _i, _vp]),
     "dsrg_crf_batch_host": (_i, [_vp, _i, _vp, _i, _vp, _pp, _vp, _i]),
@@ -49,6 +50,9 @@ SIGNATURES = {
     "dsrg_dsrg_forward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _pp, _d, _d, _vp, _vp, _vp]),
     "dsrg_dsrg_forward_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _pp, _d, _d, _vp, _vp]),
     "dsrg_crflayer_forward_dev": (_i, [_vp, _i, _vp, _vp, _pp, _vp, _vp, _vp]),
+    "dsrg_crflayer_forward_host": (_i, [_vp, _i, _vp, _vp, _pp, _vp, _vp]),
+    "dsrg_seedloss_forward_host": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "dsrg_seedloss_backward_host": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp]),
     "dsrg_seedloss_forward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "dsrg_seedloss_backward_dev": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "dsrg_profile_tag_count": (_i, []),

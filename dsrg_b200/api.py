@@ -81,6 +81,9 @@ class Engine(object):
     def device_bytes(self):
         return self._L.dsrg_engine_device_bytes(self.h)
 
+    def set_host_chunk(self, images):
+        check(self._L.dsrg_engine_set_host_chunk(self.h, int(images)))
+
     def take_launch_count(self):
         return int(self._L.dsrg_engine_take_launch_count(self.h))
 
@@ -155,6 +158,29 @@ class Engine(object):
                                              float(th1), float(th2), _hptr(seeds_out, np.float32),
                                              _hptr(crf_out, np.float32)))
         return seeds_out
+
+    def crflayer_forward_host(self, probs, image, params, log_out=None, result=None):
+        B = probs.shape[0]
+        if log_out is None:
+            log_out = np.empty(probs.shape, np.float32)
+        check(self._L.dsrg_crflayer_forward_host(self.h, B, _hptr(probs, np.float32), _hptr(image, np.uint8),
+                                                 C.byref(params), _hptr(log_out, np.float32), _hptr(result, np.float32)))
+        return log_out
+
+    def seedloss_forward_host(self, probs, seeds):
+        """(term_bg, term_fg) local sums; loss = -(term_bg + term_fg) / N_global."""
+        terms = np.zeros(2, np.float32)
+        check(self._L.dsrg_seedloss_forward_host(self.h, probs.shape[0], _hptr(probs, np.float32),
+                                                 _hptr(seeds, np.float32), _hptr(terms, np.float32)))
+        return terms
+
+    def seedloss_backward_host(self, probs, seeds, n_global=None, top_diff=1.0, grad=None):
+        if grad is None:
+            grad = np.empty(probs.shape, np.float32)
+        check(self._L.dsrg_seedloss_backward_host(self.h, probs.shape[0], int(n_global or probs.shape[0]),
+                                                  _hptr(probs, np.float32), _hptr(seeds, np.float32),
+                                                  float(top_diff), _hptr(grad, np.float32)))
+        return grad
 
     # ---- per-kernel timing ----
     def profile(self, enable):

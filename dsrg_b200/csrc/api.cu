@@ -301,6 +301,8 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     rc |= dalloc(e, &e->dev_err, 1);
     if (!rc && cudaMemset(e->dev_err, 0, sizeof(int)) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
+    if (!rc && cudaStreamCreateWithFlags(&e->in_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
+    if (!rc && cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
     if (rc) {
         dsrg_engine_destroy((dsrg_engine *)e);
         return nullptr;
@@ -321,6 +323,9 @@ void dsrg_engine_destroy(dsrg_engine *h) {
                     e->st_cues, e->st_labels, e->st_image, e->st_lmap};
     for (void *p : ptrs) cudaFree(p);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->in_stream) cudaStreamDestroy(e->in_stream);
+    if (e->out_stream) cudaStreamDestroy(e->out_stream);
+    for (auto ev : e->pipe_events) cudaEventDestroy(ev);
     for (auto &r : e->prof_recs) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
@@ -347,6 +352,13 @@ static const char *kTagNames[T_COUNT] = {
 int dsrg_profile_tag_count(void) { return T_COUNT; }
 
 const char *dsrg_profile_tag_name(int tag) { return (tag >= 0 && tag < T_COUNT) ? kTagNames[tag] : ""; }
+
+int dsrg_engine_set_host_chunk(dsrg_engine *h, int images) {
+    Engine *e = (Engine *)h;
+    if (!e || images < 0) return DSRG_E_INVALID;
+    e->host_chunk = images;
+    return DSRG_OK;
+}
 
 int dsrg_engine_profile(dsrg_engine *h, int enable) {
     Engine *e = (Engine *)h;
@@ -494,6 +506,9 @@ int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *pro
     return srg_run(e, B, labels, e->Qcur, cues, th1, th2, 1, seeds_out, nullptr, s);
 }
 
+// Host-buffer version of the full pass.  The batch is cut into chunks that flow through three
+// streams (H2D | kernels | D2H) so that PCIe traffic in both directions overlaps the compute of the
+// neighbouring chunks; results are identical to one big launch because images are independent.
 int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels, float *probs,
                            const float *cues, const uint8_t *image, const dsrg_crf_params *params,
                            double th1, double th2, float *seeds_out, float *crf_out) {
@@ -505,24 +520,41 @@ int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels, float *pr
         return DSRG_E_INVALID;
     }
     if ((rc = ensure_staging(e))) return rc;
-    cudaStream_t s = e->own_stream;
-    const size_t n = (size_t)B * e->M * e->N;
-    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_labels, labels, (size_t)B * e->M * sizeof(float), cudaMemcpyHostToDevice, s));
-    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
-    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, cues, n * sizeof(float), cudaMemcpyHostToDevice, s));
-    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image, image, (size_t)B * e->N * 3, cudaMemcpyHostToDevice, s));
-    // seeds land in st_out; the optional raw marginals are exported into st_cues afterwards
-    // (the SRG has consumed the cues by then; same stream, so ordered)
-    rc = dsrg_dsrg_forward_dev(h, B, e->st_labels, e->st_unary, e->st_cues, e->st_image, params, th1,
-                               th2, e->st_out, nullptr, s);
-    if (rc) return rc;
-    DSRG_CUDA_TRY(cudaMemcpyAsync(seeds_out, e->st_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    // the reference mutates the probs blob in place (pylayers.py:312): hand the clamped values back
-    DSRG_CUDA_TRY(cudaMemcpyAsync(probs, e->st_unary, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (crf_out) {
-        if ((rc = meanfield_export(e, B, e->st_cues, DSRG_LAYOUT_NCHW, s))) return rc;
-        DSRG_CUDA_TRY(cudaMemcpyAsync(crf_out, e->st_cues, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    const int chunk = e->host_chunk > 0 ? e->host_chunk : 16;
+    const int nchunks = (B + chunk - 1) / chunk;
+    while ((int)e->pipe_events.size() < 2 * nchunks) {
+        cudaEvent_t ev;
+        DSRG_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->pipe_events.push_back(ev);
     }
+    cudaStream_t s_in = e->in_stream, s = e->own_stream, s_out = e->out_stream;
+    const size_t img_elems = (size_t)e->M * e->N;
+    for (int c = 0; c < nchunks; c++) {
+        const int b0 = c * chunk, nb = (B - b0 < chunk) ? B - b0 : chunk;
+        const size_t o = (size_t)b0 * img_elems, n = (size_t)nb * img_elems;
+        DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_labels + (size_t)b0 * e->M, labels + (size_t)b0 * e->M,
+                                      (size_t)nb * e->M * sizeof(float), cudaMemcpyHostToDevice, s_in));
+        DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary + o, probs + o, n * sizeof(float), cudaMemcpyHostToDevice, s_in));
+        DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues + o, cues + o, n * sizeof(float), cudaMemcpyHostToDevice, s_in));
+        DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image + (size_t)b0 * e->N * 3, image + (size_t)b0 * e->N * 3,
+                                      (size_t)nb * e->N * 3, cudaMemcpyHostToDevice, s_in));
+        DSRG_CUDA_TRY(cudaEventRecord(e->pipe_events[2 * c], s_in));
+        DSRG_CUDA_TRY(cudaStreamWaitEvent(s, e->pipe_events[2 * c], 0));
+        rc = dsrg_dsrg_forward_dev(h, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o,
+                                   e->st_image + (size_t)b0 * e->N * 3, params, th1, th2, e->st_out + o, nullptr, s);
+        if (rc) return rc;
+        if (crf_out) {  // raw marginals of this chunk, parked in the (now consumed) cues staging area
+            if ((rc = meanfield_export(e, nb, e->st_cues + o, DSRG_LAYOUT_NCHW, s))) return rc;
+        }
+        DSRG_CUDA_TRY(cudaEventRecord(e->pipe_events[2 * c + 1], s));
+        DSRG_CUDA_TRY(cudaStreamWaitEvent(s_out, e->pipe_events[2 * c + 1], 0));
+        DSRG_CUDA_TRY(cudaMemcpyAsync(seeds_out + o, e->st_out + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        // the reference mutates the probs blob in place (pylayers.py:312): hand the clamped values back
+        DSRG_CUDA_TRY(cudaMemcpyAsync(probs + o, e->st_unary + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        if (crf_out)
+            DSRG_CUDA_TRY(cudaMemcpyAsync(crf_out + o, e->st_cues + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    }
+    DSRG_CUDA_TRY(cudaStreamSynchronize(s_out));
     return check_device_flag(e, s);
 }
 
@@ -540,6 +572,68 @@ int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t
     rc = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
     if (rc) return rc;
     return meanfield_export_renorm(e, B, result, log_out, s);
+}
+
+int dsrg_crflayer_forward_host(dsrg_engine *h, int B, float *probs, const uint8_t *image,
+                               const dsrg_crf_params *params, float *log_out, float *result) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!probs || !image || !log_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    if ((rc = ensure_staging(e))) return rc;
+    cudaStream_t s = e->own_stream;
+    const size_t n = (size_t)B * e->M * e->N;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image, image, (size_t)B * e->N * 3, cudaMemcpyHostToDevice, s));
+    rc = dsrg_crflayer_forward_dev(h, B, e->st_unary, e->st_image, params, e->st_out, result ? e->st_cues : nullptr, s);
+    if (rc) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(log_out, e->st_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(probs, e->st_unary, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (result) DSRG_CUDA_TRY(cudaMemcpyAsync(result, e->st_cues, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    return check_device_flag(e, s);
+}
+
+int dsrg_seedloss_forward_host(dsrg_engine *h, int B, const float *probs, const float *seeds,
+                               float *terms_out) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!probs || !seeds || !terms_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    if ((rc = ensure_staging(e))) return rc;
+    cudaStream_t s = e->own_stream;
+    const size_t n = (size_t)B * e->M * e->N;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, seeds, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    if ((rc = seedloss_forward(e, B, e->st_unary, e->st_cues, e->st_labels, s))) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(terms_out, e->st_labels, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DSRG_CUDA_TRY(cudaStreamSynchronize(s));
+    return DSRG_OK;
+}
+
+int dsrg_seedloss_backward_host(dsrg_engine *h, int B, int n_global, const float *probs,
+                                const float *seeds, float top_diff, float *grad) {
+    Engine *e = (Engine *)h;
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!probs || !seeds || !grad || n_global < 1) {
+        set_error("bad argument");
+        return DSRG_E_INVALID;
+    }
+    if ((rc = ensure_staging(e))) return rc;
+    cudaStream_t s = e->own_stream;
+    const size_t n = (size_t)B * e->M * e->N;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, seeds, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    if ((rc = seedloss_backward(e, B, n_global, e->st_unary, e->st_cues, top_diff, e->st_out, s))) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(grad, e->st_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DSRG_CUDA_TRY(cudaStreamSynchronize(s));
+    return DSRG_OK;
 }
 
 int dsrg_seedloss_forward_dev(dsrg_engine *h, int B, const float *probs, const float *seeds,

@@ -125,7 +125,9 @@ struct Engine {
     float *st_unary = nullptr, *st_out = nullptr, *st_cues = nullptr, *st_labels = nullptr;
     uint8_t *st_image = nullptr;
     int32_t *st_lmap = nullptr;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    std::vector<cudaEvent_t> pipe_events;
+    int host_chunk = 16;  // images per pipeline stage of the *_host entry points
     int *dev_err = nullptr;  // device-side error flag
     // per-kernel event timing (off by default)
     bool prof = false;

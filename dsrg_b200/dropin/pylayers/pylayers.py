@@ -1,0 +1,223 @@
+"""Drop-in Caffe Python layers for DSRG's pixel-labelling hot path, B200-backed.
+
+Same class names, bottoms/tops, ``param_str`` keys, side effects and error behaviour as the
+reference's pylayers/pylayers/pylayers.py, so ``python_param { module: 'pylayers' layer: ... }``
+in train-s.prototxt:746-812 keeps working:
+
+* ``CRFLayer``               (pylayers.py:54-92)   -> dsrg_crflayer_forward_host
+* ``DSRGLayer``              (pylayers.py:277-344) -> dsrg_dsrg_forward_host
+* ``BalancedSeedLossLayer``  (pylayers.py:120-152) -> dsrg_seedloss_{forward,backward}_host
+* ``generate_seed_step``     (pylayers.py:237-275) -> dsrg_srg_batch_host (batch of one)
+* ``SoftmaxLayer`` / ``ConstrainLossLayer`` (pylayers.py:23-51, :154-180): the producer and the
+  other consumer of the hot path's blobs, restated in numpy on the host for now
+  so that the module covers every Python layer train-s.prototxt names except the data layer.
+
+The blobs Caffe hands to a Python layer are host numpy views, so the ``*_host`` entry points of
+the C ABI are used: one H2D of the bottoms and one D2H of the tops per call, everything else on
+the GPU.  There is no multiprocessing.Pool (pylayers.py:292) and no CPU fallback.
+"""
+import numpy as np
+import yaml
+from scipy.ndimage import zoom
+
+import caffe  # the layers subclass caffe.Layer exactly like the reference (pylayers.py:1)
+
+from dsrg_b200 import api as _api
+
+min_prob = 0.0001  # pylayers.py:20
+
+_ENGINES = {}
+
+
+def _engine(n, c, h, w):
+    """One engine per blob shape, created on first use and kept (layers are long-lived)."""
+    key = (int(n), int(c), int(h), int(w))
+    if key not in _ENGINES:
+        _ENGINES[key] = _api.Engine(key[0], key[2], key[3], key[1])
+    return _ENGINES[key]
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _prepare_image(im, h, w):
+    """pylayers.py:70-75 / :315-319: bilinear zoom to the map size, + mean pixel, np.round; the CRF
+    then casts to ubyte (CRF.py:32)."""
+    mean_pixel = np.array([104.0, 117.0, 123.0])
+    im = zoom(im, (1.0, 1.0, float(h) / im.shape[2], float(w) / im.shape[3]), order=1)
+    im = np.transpose(im, [0, 2, 3, 1])
+    im = im + mean_pixel[None, None, None, :]
+    im = np.round(im)
+    return np.ascontiguousarray(im.astype('ubyte'))
+
+
+def _clamped_writeback(blob_data, probs):
+    """The reference clamps the bottom blob in place (pylayers.py:67, :312); the device did the
+    clamp on its copy, so hand the values back to the blob."""
+    blob_data[...] = probs
+
+
+class SoftmaxLayer(caffe.Layer):
+    """pylayers.py:23-51 (numpy restatement of the Theano graph)."""
+
+    def setup(self, bottom, top):
+        if len(bottom) != 1:
+            raise Exception("Need two inputs to compute distance.")
+
+    def reshape(self, bottom, top):
+        top[0].reshape(*bottom[0].data.shape)
+
+    @staticmethod
+    def _softmax(preds):
+        e = np.exp(preds - np.max(preds, axis=1, keepdims=True))
+        return e / np.sum(e, axis=1, keepdims=True)
+
+    def forward(self, bottom, top):
+        s = self._softmax(bottom[0].data[...].astype(np.float32))
+        probs = s + np.float32(min_prob)
+        top[0].data[...] = probs / np.sum(probs, axis=1, keepdims=True)
+
+    def backward(self, top, prop_down, bottom):
+        s = self._softmax(bottom[0].data[...].astype(np.float32))
+        z = np.sum(s + np.float32(min_prob), axis=1, keepdims=True)   # == 1 + C*min_prob
+        # probs = (s + m) / z with z = sum_c (s_c + m): d sum(probs*top_diff) / d s
+        gs = top[0].diff[...] / z - np.sum(top[0].diff[...] * (s + np.float32(min_prob)), axis=1, keepdims=True) / (z * z)
+        bottom[0].diff[...] = s * (gs - np.sum(gs * s, axis=1, keepdims=True))
+
+
+class CRFLayer(caffe.Layer):
+    """pylayers.py:54-92."""
+
+    def setup(self, bottom, top):
+        if len(bottom) != 2:
+            raise Exception("The layer needs two inputs!")
+
+    def reshape(self, bottom, top):
+        top[0].reshape(*bottom[0].data.shape)
+
+    def forward(self, bottom, top):
+        n, c, h, w = bottom[0].data.shape
+        probs = _f32(bottom[0].data)
+        im = _prepare_image(bottom[1].data[...], h, w)
+        eng = _engine(n, c, h, w)
+        log_out = np.empty((n, c, h, w), np.float32)
+        self.result = np.empty((n, c, h, w), np.float32)
+        eng.crflayer_forward_host(probs, im, _api.crf_params(12.0), log_out, self.result)  # scale_factor=12.0 (:82)
+        _clamped_writeback(bottom[0].data, probs)
+        top[0].data[...] = log_out
+
+    def backward(self, top, prop_down, bottom):
+        grad = (1 - self.result) * top[0].diff[...]
+        bottom[0].diff[...] = grad
+
+
+class BalancedSeedLossLayer(caffe.Layer):
+    """pylayers.py:120-152."""
+
+    def setup(self, bottom, top):
+        if len(bottom) != 2:
+            raise Exception("The layer needs two inputs!")
+
+    def reshape(self, bottom, top):
+        top[0].reshape(1)
+
+    def forward(self, bottom, top):
+        n, c, h, w = bottom[0].data.shape
+        terms = _engine(n, c, h, w).seedloss_forward_host(_f32(bottom[0].data), _f32(bottom[1].data))
+        terms, n_global = _allreduce_terms(terms, n)
+        top[0].data[...] = -(float(terms[0]) + float(terms[1])) / n_global
+
+    def backward(self, top, prop_down, bottom):
+        n, c, h, w = bottom[0].data.shape
+        _, n_global = _allreduce_terms(None, n)
+        # like the reference (pylayers.py:150-152) the incoming top diff is NOT applied
+        bottom[0].diff[...] = _engine(n, c, h, w).seedloss_backward_host(_f32(bottom[0].data), _f32(bottom[1].data),
+                                                                           n_global=n_global, top_diff=1.0)
+
+
+def _allreduce_terms(terms, n_local):
+    """One process per GPU: the balanced loss is a mean over the GLOBAL batch, so the two local sums
+    are all-reduced (the path's only collective, dsrg_b200/shard.py).  Single process: identity."""
+    from dsrg_b200 import shard
+    return shard.allreduce_loss_terms(terms, n_local)
+
+
+class ConstrainLossLayer(caffe.Layer):
+    """pylayers.py:154-180 (numpy restatement of the Theano graph)."""
+
+    def setup(self, bottom, top):
+        if len(bottom) != 2:
+            raise Exception("The layer needs two inputs!")
+
+    def reshape(self, bottom, top):
+        top[0].reshape(1)
+
+    def forward(self, bottom, top):
+        probs = bottom[0].data[...].astype(np.float32)
+        ps = np.exp(bottom[1].data[...].astype(np.float32))
+        top[0].data[...] = np.mean(np.sum(ps * np.log(np.clip(ps / probs, 0.05, 20)), axis=1))
+
+    def backward(self, top, prop_down, bottom):
+        probs = bottom[0].data[...].astype(np.float32)
+        ps = np.exp(bottom[1].data[...].astype(np.float32))
+        ratio = ps / probs
+        inside = ((ratio >= 0.05) & (ratio <= 20)).astype(np.float32)   # gradient of clip
+        cnt = float(probs.shape[0] * probs.shape[2] * probs.shape[3])   # T.mean over (n, h, w)
+        bottom[0].diff[...] = -(ps / probs) * inside / cnt
+        bottom[1].diff[...] = ps * (np.log(np.clip(ratio, 0.05, 20)) + inside) / cnt
+
+
+def generate_seed_step(item):
+    """pylayers.py:237-275 for ONE image: item = [labels (C,), seed_c (C,H,W), probs (C,H,W), th1, th2].
+    Mutates and returns seed_c like the reference."""
+    labels, seed_c, probs_refinement, th1, th2 = item
+    c, h, w = seed_c.shape
+    eng = _engine(1, c, h, w)
+    # the reference compares float64 values; float32 inputs are compared exactly as given
+    p32 = _f32(probs_refinement)[None]
+    if not np.array_equal(p32[0].astype(np.float64), np.asarray(probs_refinement, np.float64)):
+        raise ValueError("generate_seed_step: probs must be representable in float32 "
+                         "(use DSRGLayer / dsrg_dsrg_forward for the fused float64 renormalisation)")
+    out = eng.srg_host(_f32(labels)[None], p32, _f32(seed_c)[None], th1, th2)
+    seed_c[...] = out[0]
+    return seed_c
+
+
+class DSRGLayer(caffe.Layer):
+    """pylayers.py:277-344."""
+
+    def setup(self, bottom, top):
+        if len(bottom) != 4:
+            raise Exception("The layer needs four inputs!")
+        # parse the layer parameter string, which must be valid YAML (pylayers.py:284-291)
+        layer_params = yaml.safe_load(self.param_str)
+        self._th1 = layer_params['th1']
+        self._th2 = layer_params['th2']
+        if 'iters' not in layer_params:
+            layer_params['iters'] = -1
+        self._max_iters = layer_params['iters']
+        self._iter_index = 0
+
+    def reshape(self, bottom, top):
+        top[0].reshape(*bottom[1].data.shape)
+
+    def forward(self, bottom, top):
+        img_labels, probs, cues, im = bottom[0].data, bottom[1].data, bottom[2].data, bottom[3].data
+        seed_c = self.generate_seed(img_labels, probs, cues, im)
+        self._iter_index = self._iter_index + 1
+        top[0].data[...] = seed_c
+
+    def backward(self, top, prop_down, bottom):
+        bottom[1].diff[...] = top[0].diff
+
+    def generate_seed(self, labels, probs, cues, im):
+        """refinement (pylayers.py:310-331) + SRG over the batch (:333-344), fused on the device."""
+        num, channels, height, width = probs.shape
+        p = _f32(probs)
+        image = _prepare_image(im, height, width)
+        eng = _engine(num, channels, height, width)
+        seeds = eng.dsrg_forward_host(_f32(labels).reshape(num, channels), p, _f32(cues), image,
+                                      _api.crf_params(12.0), self._th1, self._th2)
+        _clamped_writeback(probs, p)
+        return seeds

@@ -74,6 +74,9 @@ typedef struct dsrg_engine dsrg_engine;
 dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M);
 void dsrg_engine_destroy(dsrg_engine *e);
 size_t dsrg_engine_device_bytes(const dsrg_engine *e); /* bytes of HBM held by the engine */
+/* The *_host full-pass entry point pipelines the batch in chunks of `images` (default 16) through
+ * H2D | kernels | D2H streams; 0 restores the default. */
+int dsrg_engine_set_host_chunk(dsrg_engine *e, int images);
 /* Kernel launches issued by this engine since the last call (bench.py's gpu_launches). */
 long long dsrg_engine_take_launch_count(dsrg_engine *e);
 
@@ -148,6 +151,10 @@ int dsrg_crflayer_forward_dev(dsrg_engine *e, int B, float *probs_dev, const uin
                               const dsrg_crf_params *params, float *log_out_dev,
                               float *result_dev, void *stream);
 
+int dsrg_crflayer_forward_host(dsrg_engine *e, int B, float *probs_host, const uint8_t *image_host,
+                               const dsrg_crf_params *params, float *log_out_host,
+                               float *result_host);
+
 /*
  * BalancedSeedLossLayer (pylayers.py:120-152).  Forward writes the LOCAL sums
  *   terms_out[0] = sum_n S_bg(n) / max(cnt_bg(n), 1e-4),  terms_out[1] = same for fg
@@ -160,6 +167,11 @@ int dsrg_seedloss_forward_dev(dsrg_engine *e, int B, const float *probs_dev,
 int dsrg_seedloss_backward_dev(dsrg_engine *e, int B, int n_global, const float *probs_dev,
                                const float *seeds_dev, float top_diff, float *grad_out_dev,
                                void *stream);
+
+int dsrg_seedloss_forward_host(dsrg_engine *e, int B, const float *probs_host,
+                               const float *seeds_host, float *terms_out_host /* 2 floats */);
+int dsrg_seedloss_backward_host(dsrg_engine *e, int B, int n_global, const float *probs_host,
+                                const float *seeds_host, float top_diff, float *grad_out_host);
 
 /* Optional per-kernel timing for the roofline report: while enabled every kernel launch of the
  * engine is bracketed by CUDA events on its launching stream.  dsrg_engine_profile_read()

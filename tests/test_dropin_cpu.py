@@ -1,0 +1,110 @@
+"""CPU tests of the drop-in boundary: the `pylayers` / `krahenbuhl2013` modules import under a fake
+caffe, expose the reference's names and honour its setup/reshape/error contract.  No GPU compute."""
+import inspect
+
+import numpy as np
+import pytest
+
+import fake_caffe
+
+fake_caffe.install()
+import krahenbuhl2013  # noqa: E402
+import pylayers  # noqa: E402
+
+
+def test_module_surface_matches_reference_names():
+    for name in ("SoftmaxLayer", "CRFLayer", "DSRGLayer", "BalancedSeedLossLayer", "ConstrainLossLayer",
+                 "generate_seed_step", "min_prob"):
+        assert hasattr(pylayers, name), name
+    assert pylayers.min_prob == 0.0001
+    sig = inspect.signature(krahenbuhl2013.CRF)
+    assert list(sig.parameters) == ["image", "unary", "maxiter", "scale_factor", "color_factor"]
+    assert [sig.parameters[k].default for k in ("maxiter", "scale_factor", "color_factor")] == [10, 1.0, 13]
+    from krahenbuhl2013.wrapper import DenseCRF
+    for m in ("set_unary_energy", "add_pairwise_energy", "map", "inference"):
+        assert callable(getattr(DenseCRF, m))
+    for cls in (pylayers.CRFLayer, pylayers.DSRGLayer, pylayers.BalancedSeedLossLayer):
+        for m in ("setup", "reshape", "forward", "backward"):
+            assert callable(getattr(cls, m))
+
+
+@pytest.mark.parametrize("cls,need", [(pylayers.CRFLayer, 2), (pylayers.DSRGLayer, 4),
+                                      (pylayers.BalancedSeedLossLayer, 2), (pylayers.ConstrainLossLayer, 2),
+                                      (pylayers.SoftmaxLayer, 1)])
+def test_wrong_bottom_count_raises_plain_exception(cls, need):
+    layer = cls()
+    layer.param_str = "{'th1': 0.99, 'th2': 0.85}"
+    with pytest.raises(Exception):
+        layer.setup([fake_caffe.Blob()] * (need + 1), [fake_caffe.Blob()])
+
+
+def test_dsrg_layer_param_str_and_reshape():
+    layer = pylayers.DSRGLayer()
+    layer.param_str = "{'th1': 0.99, 'th2': 0.85}"           # train-s.prototxt:783
+    bottom = [fake_caffe.Blob(np.zeros(s)) for s in ((2, 1, 1, 21), (2, 21, 41, 41), (2, 21, 41, 41), (2, 3, 321, 321))]
+    top = [fake_caffe.Blob()]
+    layer.setup(bottom, top)
+    assert (layer._th1, layer._th2, layer._max_iters, layer._iter_index) == (0.99, 0.85, -1, 0)
+    layer.reshape(bottom, top)
+    assert top[0].data.shape == (2, 21, 41, 41)
+    top[0].diff[...] = 3.0
+    layer.backward(top, [True], bottom)                        # pylayers.py:307-308
+    assert np.all(bottom[1].diff == 3.0)
+    layer2 = pylayers.DSRGLayer()
+    layer2.param_str = "{'th1': 0.9, 'th2': 0.8, 'iters': 7}"
+    layer2.setup(bottom, top)
+    assert layer2._max_iters == 7
+
+
+def test_image_preparation_follows_reference():
+    from oracle import crf_oracle
+    rng = np.random.RandomState(0)
+    im = (rng.rand(2, 3, 64, 48) * 255 - np.array([104.0, 117.0, 123.0])[None, :, None, None]).astype(np.float32)
+    want = crf_oracle.prepare_image(im, 9, 7)
+    from pylayers import pylayers as impl
+    got = impl._prepare_image(im, 9, 7)
+    assert got.dtype == np.uint8 and np.array_equal(got, want.astype('ubyte'))
+
+
+def _num_grad(f, x, idx, eps=1e-3):
+    xp, xm = x.copy(), x.copy()
+    xp[idx] += eps
+    xm[idx] -= eps
+    return (f(xp) - f(xm)) / (2 * eps)
+
+
+def test_softmax_layer_numpy_forward_backward():
+    rng = np.random.RandomState(1)
+    x = rng.randn(2, 5, 3, 4).astype(np.float32)
+    layer, bottom, top = fake_caffe.run_layer(pylayers.SoftmaxLayer, [x])
+    p = top[0].data
+    np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-6)
+    e = np.exp(x - x.max(1, keepdims=True))
+    ref = e / e.sum(1, keepdims=True) + 1e-4
+    np.testing.assert_allclose(p, ref / ref.sum(1, keepdims=True), rtol=1e-5)
+    g = rng.randn(*x.shape).astype(np.float32)
+    top[0].diff[...] = g
+    layer.backward(top, [True], bottom)
+
+    def f(xx):
+        ee = np.exp(xx - xx.max(1, keepdims=True))
+        pp = ee / ee.sum(1, keepdims=True) + 1e-4
+        return float(np.sum(pp / pp.sum(1, keepdims=True) * g))
+    for idx in [(0, 1, 2, 3), (1, 4, 0, 0)]:
+        assert abs(_num_grad(f, x.astype(np.float64), idx, 1e-4) - bottom[0].diff[idx]) < 2e-3
+
+
+def test_constrain_loss_layer_numpy_forward_backward():
+    rng = np.random.RandomState(2)
+    p = rng.rand(2, 4, 3, 3).astype(np.float32) * 0.8 + 0.1
+    ls = np.log(rng.rand(2, 4, 3, 3).astype(np.float32) * 0.8 + 0.1)
+    layer, bottom, top = fake_caffe.run_layer(pylayers.ConstrainLossLayer, [p, ls])
+
+    def f(pp, ll):
+        ps = np.exp(ll)
+        return float(np.mean(np.sum(ps * np.log(np.clip(ps / pp, 0.05, 20)), axis=1)))
+    assert abs(float(top[0].data[0]) - f(p.astype(np.float64), ls.astype(np.float64))) < 1e-5
+    layer.backward(top, [True, True], bottom)
+    for idx in [(0, 1, 2, 2), (1, 3, 0, 1)]:
+        assert abs(_num_grad(lambda q: f(q, ls.astype(np.float64)), p.astype(np.float64), idx, 1e-5) - bottom[0].diff[idx]) < 1e-3
+        assert abs(_num_grad(lambda q: f(p.astype(np.float64), q), ls.astype(np.float64), idx, 1e-5) - bottom[1].diff[idx]) < 1e-3

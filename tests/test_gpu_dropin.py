@@ -1,0 +1,92 @@
+"""GPU tests of the drop-in boundary: the reference-shaped Python layers and the krahenbuhl2013
+module, driven through a fake caffe, against the CPU oracles."""
+import numpy as np
+import pytest
+
+import fake_caffe
+
+fake_caffe.install()
+import krahenbuhl2013  # noqa: E402
+import pylayers  # noqa: E402
+from dsrg_b200 import synth  # noqa: E402
+from oracle import crf_oracle, loss_oracle, srg_oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def training_blobs(n=3, hw=41, big=97, start=900):
+    batch = synth.make_batch(n, hw, hw, cues="cam", image="smooth", start=start)
+    rng = np.random.RandomState(start)
+    images = (rng.rand(n, 3, big, big) * 255.0 - np.array([104.0, 117.0, 123.0])[None, :, None, None]).astype(np.float32)
+    # smooth them a little so the zoomed image is not pure noise
+    images = (images + np.roll(images, 1, 2) + np.roll(images, 1, 3)) / 3
+    probs = batch["probs"].copy()
+    probs[0, 5, :4, :4] = 1e-6   # exercises the in-place clamp (pylayers.py:312)
+    return batch["labels"].reshape(n, 1, 1, -1), probs, batch["cues"], images
+
+
+def test_krahenbuhl2013_crf_function(torch_cuda):
+    p = synth.make_problem(33, 45, 38, image="smooth")
+    pr = np.transpose(p["probs"], (1, 2, 0)).copy()
+    pr[pr < 1e-5] = 1e-5
+    for unary, sf in ((np.log(pr), 1.0), (pr, 12.0)):
+        got = krahenbuhl2013.CRF(p["image"], unary, scale_factor=sf)
+        want = crf_oracle.CRF(p["image"], unary, scale_factor=sf)
+        assert got.shape == want.shape and got.dtype == np.float32
+        assert np.abs(got - want).max() <= 1e-4
+
+
+def test_crf_layer_forward_backward(torch_cuda):
+    labels, probs, cues, images = training_blobs()
+    layer, bottom, top = fake_caffe.run_layer(pylayers.CRFLayer, [probs, images])
+    clamped = probs.copy()
+    clamped[clamped < 1e-4] = 1e-4
+    assert np.array_equal(bottom[0].data, clamped)              # in-place side effect on the blob
+    want = crf_oracle.refinement(probs.copy(), images, 12.0)     # float64 (N,C,h,w)
+    assert np.abs(np.exp(top[0].data) - want).max() <= 1e-4
+    assert top[0].data.dtype == np.float32
+    top[0].diff[...] = 0.5
+    layer.backward(top, [True, False], bottom)
+    np.testing.assert_allclose(bottom[0].diff, (1 - want) * 0.5, atol=1e-4)
+
+
+def test_dsrg_layer_forward(torch_cuda):
+    labels, probs, cues, images = training_blobs()
+    layer, bottom, top = fake_caffe.run_layer(pylayers.DSRGLayer, [labels, probs, cues, images],
+                                              param_str="{'th1': 0.99, 'th2': 0.85}")
+    clamped = probs.copy()
+    clamped[clamped < 1e-4] = 1e-4
+    assert np.array_equal(bottom[1].data, clamped)
+    seeds = top[0].data
+    assert seeds.shape == probs.shape and set(np.unique(seeds)) <= {0.0, 1.0}
+    assert np.all(seeds >= cues)                                 # old seeds are never removed
+    # full CPU pipeline of the reference: refinement (CRF oracle) -> SRG.  The CRF marginals agree
+    # to 1e-4, so the seed maps may only differ where a marginal sits within 1e-4 of a threshold
+    ref = crf_oracle.refinement(probs.copy(), images, 12.0)
+    n = probs.shape[0]
+    mism = 0
+    for b in range(n):
+        want = srg_oracle.srg_closed_form(labels[b, 0, 0], cues[b], ref[b], 0.99, 0.85)
+        mism += int((want != seeds[b]).sum())
+    assert mism <= 1e-3 * seeds.size, mism
+    assert layer._iter_index == 1
+
+
+def test_balanced_seed_loss_layer(torch_cuda):
+    labels, probs, cues, images = training_blobs(n=4)
+    probs[probs < 1e-4] = 1e-4
+    seeds = cues.copy()
+    seeds[1, 1:] = 0
+    layer, bottom, top = fake_caffe.run_layer(pylayers.BalancedSeedLossLayer, [probs, seeds])
+    want = loss_oracle.balanced_seed_loss(probs, seeds)
+    assert abs(float(top[0].data[0]) - want) <= 1e-5 * abs(want)
+    layer.backward(top, [True, False], bottom)
+    np.testing.assert_allclose(bottom[0].diff, loss_oracle.balanced_seed_loss_grad(probs, seeds), rtol=1e-5, atol=1e-9)
+
+
+def test_generate_seed_step_function(torch_cuda):
+    p = synth.make_problem(5, 50, 40, cues="random")
+    want = srg_oracle.srg_closed_form(p["labels"], p["cues"], p["probs"], 0.99, 0.85)
+    seed_c = p["cues"].copy()
+    out = pylayers.generate_seed_step([p["labels"], seed_c, p["probs"].astype(np.float64), 0.99, 0.85])
+    assert out is seed_c and np.array_equal(out, want)

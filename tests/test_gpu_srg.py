@@ -117,3 +117,24 @@ def test_dsrg_forward_fused_pass(torch_cuda, H, W, sf, img):
     for b in range(B):
         assert np.array_equal(s2[b], srg_oracle.srg_closed_form(batch["labels"][b], batch["cues"][b], r64[b], 0.99, 0.85))
     eng.close()
+
+
+def test_dsrg_forward_host_pipelined_chunks(torch_cuda):
+    """The host entry point streams the batch in chunks over H2D | compute | D2H; chunking must not
+    change anything (images are independent): seeds stay bit-exact w.r.t. each call's own marginals."""
+    B, H, W, M, sf = 5, 48, 56, 21, 12.0
+    batch = synth.make_batch(B, H, W, cues="cam", image="smooth", start=120)
+    eng = api.Engine(B, H, W, M)
+    outs = []
+    for chunk in (2, 16):
+        eng.set_host_chunk(chunk)
+        p = batch["probs"].copy()
+        q = np.empty_like(p)
+        s = eng.dsrg_forward_host(batch["labels"], p, batch["cues"], batch["image"], api.crf_params(sf), 0.99, 0.85, crf_out=q)
+        r64 = renorm64(q)
+        for b in range(B):
+            assert np.array_equal(s[b], srg_oracle.srg_closed_form(batch["labels"][b], batch["cues"][b], r64[b], 0.99, 0.85))
+        outs.append((s, q))
+    assert np.abs(outs[0][1] - outs[1][1]).max() <= 2e-5
+    assert (outs[0][0] != outs[1][0]).mean() <= 1e-4
+    eng.close()
