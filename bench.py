@@ -74,23 +74,33 @@ def measured_peak():
 
 
 class ClockSampler(object):
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi sampling while the GPU is under load (B200_PROFILING.md clocks line).  Started
+    before the warm-up steps so that nvidia-smi's start-up latency does not eat a short timed region;
+    mark() is called at the start of the timed region and only later samples are reported when
+    there are any."""
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        self.t_mark = None
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark(self):
+        import datetime
+        self.t_mark = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.12)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -98,24 +108,25 @@ class ClockSampler(object):
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(c[1]), float(c[2]), float(c[3]), [n for n, v in zip(names, c[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         os.unlink(self.f.name)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+        timed = [r for r in rows if self.t_mark is not None and r[0] >= self.t_mark]
+        use, where = (timed, "timed region") if len(timed) >= 2 else (rows, "warm-up + timed region")
+        if use:
+            reasons = sorted(set(x for r in use for x in r[4]))
+            out = {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)),
+                   "power_w_max": float(max(r[3] for r in use)), "reasons": reasons, "samples": len(use),
+                   "sampled_during": where}
         return out
 
 
@@ -262,10 +273,13 @@ def run_b200(args, rank, local_rank, world):
         barrier()
         return ms
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     eng.take_launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        torch.cuda.synchronize()
+        sampler.mark()
     ms = timed(step, args.steps)
     clocks = sampler.stop() if sampler else None
     launches = eng.take_launch_count()

@@ -57,19 +57,14 @@ k_srg_label(const float *labels, const float *probs, const float *cues, double t
         const float *lab = labels + (size_t)b * M;
         const float *pb = probs + (size_t)b * M * N + i;
         const float *cb = cues + (size_t)b * M * N + i;
-        // optional post-CRF renormalisation in float64 (pylayers.py:328-330)
-        double s = 1.0;
-        if (renorm) {
-            s = 0.0;
-            for (int c = 0; c < M; c++) {
-                double v = (double)pb[(size_t)c * N];
-                if (v < 0.0001) v = 0.0001;
-                s += v;
-            }
-        }
-        // arg-max / max over the PRESENT classes, first index wins ties (pylayers.py:240-243)
+        // One pass over the classes.  With renorm the reference divides every clamped value by the
+        // float64 sum s (pylayers.py:328-330) before taking the arg-max over the PRESENT classes
+        // (first index wins ties, pylayers.py:240-243).  IEEE division by a common positive s is
+        // monotone and cannot merge two distinct float32-exact values (they differ by >= 2^-24
+        // relative, the quotient rounds at 2^-53), so arg-max(v/s) == arg-max(v) with identical ties;
+        // only the winner is divided.
         int cstar = -1;
-        double best = 0.0;
+        double best = 0.0, s = 0.0;
         float nseed = 0.0f;   // np.sum(seed_c[:, x, y]) (pylayers.py:268)
         float cue_at_L = 0.0f;
         for (int c = 0; c < M; c++) {
@@ -79,18 +74,17 @@ k_srg_label(const float *labels, const float *probs, const float *cues, double t
                 L = c + 1;
                 cue_at_L = cu;
             }
-            if (lab[c] == 1.0f) {
-                double v = (double)pb[(size_t)c * N];
-                if (renorm) {
-                    if (v < 0.0001) v = 0.0001;
-                    v = v / s;
-                }
-                if (cstar < 0 || v > best) {
-                    best = v;
-                    cstar = c;
-                }
+            double v = (double)pb[(size_t)c * N];
+            if (renorm) {
+                if (v < 0.0001) v = 0.0001;
+                s += v;  // sequential float64 sum over classes, like np.sum(axis=1)
+            }
+            if (lab[c] == 1.0f && (cstar < 0 || v > best)) {
+                best = v;
+                cstar = c;
             }
         }
+        if (renorm) best = best / s;
         // thresholds (pylayers.py:251-257): strict > in float64; overwrite the seed label
         if (cstar >= 0 && best > th2 && (cstar != 0 || best > th1)) {
             L = cstar + 1;
