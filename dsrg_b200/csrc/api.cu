@@ -81,9 +81,9 @@ static int lattice_alloc(Engine *e, Lattice &L, int d, int shared) {
     L.maxloc = (d == 2) ? kMaxLocSp : kMaxLocBi;
     const size_t nt = n * e->ntiles;
     rc |= dalloc(e, &L.tl_nloc, nt);
-    rc |= dalloc(e, &L.tl_rows, nt * L.maxloc);
-    rc |= dalloc(e, &L.tl_ptr, nt * (L.maxloc + 1));
-    rc |= dalloc(e, &L.tl_ent, nt * 256 * (d + 1));
+    L.entcap = 256 * (d + 1) + 3 * L.maxloc;
+    rc |= dalloc(e, &L.tl_hdr, nt * L.maxloc);
+    rc |= dalloc(e, &L.tl_pack, nt * L.entcap);
     rc |= dalloc(e, &L.tl_loc, n * (d + 1) * L.N);
     rc |= dalloc(e, &L.wn, n * (d + 1) * L.N);
     if (rc) return DSRG_E_NOMEM;
@@ -102,9 +102,8 @@ static void lattice_free(Lattice &L) {
     cudaFree(L.rowbase);
     cudaFree(L.nbr);
     cudaFree(L.tl_nloc);
-    cudaFree(L.tl_rows);
-    cudaFree(L.tl_ptr);
-    cudaFree(L.tl_ent);
+    cudaFree(L.tl_hdr);
+    cudaFree(L.tl_pack);
     cudaFree(L.tl_loc);
     cudaFree(L.wn);
 }

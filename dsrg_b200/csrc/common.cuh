@@ -56,9 +56,10 @@ struct Lattice {
     // slice run out of shared memory (see tiles.cu)
     int maxloc = 0;                // local-vertex capacity per tile; tiles beyond it use the fallback
     int32_t *tl_nloc = nullptr;    // [nimg][ntiles] distinct vertices of the tile, -1 = overflow
-    int32_t *tl_rows = nullptr;    // [nimg][ntiles][maxloc] local row ids (1-based) of those vertices
-    uint16_t *tl_ptr = nullptr;    // [nimg][ntiles][maxloc+1] CSR offsets: entries grouped by local vertex
-    uint16_t *tl_ent = nullptr;    // [nimg][ntiles][256*(d+1)] entries (pixel_in_tile << 3 | r)
+    int2 *tl_hdr = nullptr;        // [nimg][ntiles][maxloc] per local vertex: (first entry | quads<<16, local row id)
+    int2 *tl_pack = nullptr;       // [nimg][ntiles][entcap] CSR entries grouped by local vertex, segments padded
+                                   // to 4: (byte offset of the pixel's Q row in the tile, weight bits)
+    int entcap = 0;                // 256*(d+1) + 3*maxloc
     uint16_t *tl_loc = nullptr;    // [nimg][d+1][N] local vertex index of (pixel, r)
     float *wn = nullptr;           // [nimg][d+1][N] barycentric weight * norm
     float scale[5] = {0, 0, 0, 0, 0};  // elevation scale factors (permutohedral.cpp:179-182)

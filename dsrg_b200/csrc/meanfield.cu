@@ -74,15 +74,15 @@ struct TileLat {
     // direct (fallback) view
     const int32_t *off;      // [nimg][dp1][N] local row (1-based)
     const int32_t *rowbase;  // [B+1]
-    // tile-local view
+    // tile-local view (tiles.cu)
     const int32_t *tl_nloc;
-    const int32_t *tl_rows;
-    const uint16_t *tl_ptr;
-    const uint16_t *tl_ent;
+    const int2 *tl_hdr;
+    const int2 *tl_pack;
     const uint16_t *tl_loc;
     const float *wn;         // [nimg][dp1][N]
     const float *val_in;     // blurred values of the previous splat (slice source)
     float *val_out;          // zeroed values (splat target)
+    int entcap;
     int shared;
 };
 
@@ -100,16 +100,50 @@ __device__ __forceinline__ float exp_neg(float x) {
     return fmaf(e, r * kLn2, e);
 }
 
+// ---- mbarrier + 1-D bulk copy (TMA engine, SASS UBLKCP) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 24)) __trap();
+}
+// global -> shared, size and both addresses multiples of 16 bytes; completion is signalled on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 template <int MP>
 struct TileSmem {
     static constexpr int CH = MP / 4;
     static constexpr int kRows = kMaxLocSp + kMaxLocBi;
-    static constexpr int kBufF4 = (kRows * CH > 256 * CH) ? kRows * CH : 256 * CH;  // vs / qs alias
+    static constexpr int kBufF4 = (kRows * CH > 256 * CH) ? kRows * CH : 256 * CH;  // staged rows / Q alias
+    static constexpr int kEntSp = 256 * 3 + 3 * kMaxLocSp, kEntBi = 256 * 6 + 3 * kMaxLocBi;
     float4 buf[kBufF4];
-    int2 ent[9 * 256];   // (byte offset of the pixel's Q row, weight bits), CSR order
-    float wn[9 * 256];
-    int rows[kRows];
-    uint16_t ptr[kRows + 2];
+    int2 ent[kEntSp + kEntBi];  // CSR entries (byte offset of the pixel's Q row, weight bits)
+    int2 hdr[kRows];            // per local vertex (first entry | quads << 16, global row)
+    uint64_t bar;
 };
 
 // slice one lattice from the staged rows (shared memory): t += coef * sum_r wn_r * row_r
@@ -152,10 +186,10 @@ __device__ __forceinline__ void tile_slice_global(const float4 *vin, const int32
     }
 }
 
-// CSR splat of one lattice: warp per local vertex, lane = (entry slot 0..3, label quad 0..MP/4-1)
+// CSR splat of one lattice: warp per local vertex, lane = (entry slot 0..3, label quad 0..MP/4-1);
+// segments are padded to multiples of four entries, so every slot runs the same trip count
 template <int MP>
-__device__ __forceinline__ void tile_splat_csr(float4 *vout, int nloc, const uint16_t *ptr_s,
-                                               const int2 *ent_s, const int *rows_s,
+__device__ __forceinline__ void tile_splat_csr(float4 *vout, int nloc, const int2 *hdr_s, const int2 *ent_s,
                                                const unsigned char *qs_bytes) {
     constexpr int CH = MP / 4;
     static_assert(4 * CH <= 32, "lane mapping");
@@ -164,12 +198,14 @@ __device__ __forceinline__ void tile_splat_csr(float4 *vout, int nloc, const uin
     const bool act = es < 4;
     const unsigned char *qbase = qs_bytes + cq * 16;
     for (int lv = warp; lv < nloc; lv += 8) {
-        const int beg = ptr_s[lv], end = ptr_s[lv + 1];
+        const int2 h = hdr_s[lv];
+        const int n4 = h.x >> 16;
+        const int2 *ep = ent_s + (h.x & 0xffff) + es;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
 #pragma unroll 2
-            for (int e = beg + es; e < end; e += 4) {
-                const int2 en = ent_s[e];
+            for (int it = 0; it < n4; ++it, ep += 4) {
+                const int2 en = *ep;
                 const float w = __int_as_float(en.y);
                 const float4 q = *reinterpret_cast<const float4 *>(qbase + en.x);
                 a.x = fmaf(w, q.x, a.x);
@@ -187,7 +223,7 @@ __device__ __forceinline__ void tile_splat_csr(float4 *vout, int nloc, const uin
         a.y += __shfl_down_sync(0xffffffffu, a.y, CH);
         a.z += __shfl_down_sync(0xffffffffu, a.z, CH);
         a.w += __shfl_down_sync(0xffffffffu, a.w, CH);
-        if (lane < CH) atomicAdd(vout + (size_t)rows_s[lv] * CH + cq, a);
+        if (lane < CH) atomicAdd(vout + (size_t)h.y * CH + cq, a);
     }
 }
 
@@ -211,8 +247,10 @@ __global__ void __launch_bounds__(256, 3)
 k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
           float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles) {
     constexpr int CH = MP / 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem<MP> &sm = *reinterpret_cast<TileSmem<MP> *>(smem_raw);
+    constexpr int kRowBytes = MP * 4;
+    using SM = TileSmem<MP>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
     const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int x = tx * kTileW + (tid & 31), y = ty * kTileH + (tid >> 5);
@@ -225,67 +263,59 @@ k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, Til
     const int n_sp = fb_sp ? 0 : nl_sp, n_bi = fb_bi ? 0 : nl_bi;
     const int base_sp = sp.rowbase[b], base_bi = bi.rowbase[b];
     float4 *vs_sp = sm.buf, *vs_bi = sm.buf + kMaxLocSp * CH;
-    int *rows_sp = sm.rows, *rows_bi = sm.rows + kMaxLocSp;
+    int2 *hdr_sp = sm.hdr, *hdr_bi = sm.hdr + kMaxLocSp;
+    int2 *ent_sp = sm.ent, *ent_bi = sm.ent + SM::kEntSp;
     const size_t strideN = (size_t)N;
     const size_t px_sp = (size_t)sb_sp * 3 * N + pix, px_bi = (size_t)sb_bi * 6 * N + pix;
 
-    // ---- phase A: per-pixel data (thread = pixel) and the tile's row list ----
+    // ---- asynchronous staging: every local vertex's value row (96 B) and the two CSR entry blocks
+    // are pulled into shared memory by the bulk-copy engine while the threads load their per-pixel data
+    const int n_copies = (MODE != MODE_FIRST ? n_sp + n_bi : 0) + (MODE != MODE_LAST ? (n_sp > 0) + (n_bi > 0) : 0);
+    if (tid == 0) {
+        mbar_init(&sm.bar, n_copies > 0 ? n_copies : 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    for (int i = tid; i < n_sp + n_bi; i += 256) {  // up to 128 + 256 local vertices
+        const bool is_sp = i < n_sp;
+        const int lv = is_sp ? i : i - n_sp;
+        const int2 h = is_sp ? sp.tl_hdr[ti_sp * kMaxLocSp + lv] : bi.tl_hdr[ti_bi * kMaxLocBi + lv];
+        const int row = (is_sp ? base_sp : base_bi) + h.y;
+        (is_sp ? hdr_sp : hdr_bi)[lv] = make_int2(h.x, row);
+        if (MODE != MODE_FIRST) {
+            mbar_arrive_expect_tx(&sm.bar, kRowBytes);
+            bulk_g2s((is_sp ? vs_sp : vs_bi) + lv * CH, (is_sp ? sp.val_in : bi.val_in) + (size_t)row * MP,
+                     kRowBytes, &sm.bar);
+        }
+        if (MODE != MODE_LAST && lv == (is_sp ? n_sp : n_bi) - 1) {  // the last segment tells the block's length
+            const uint32_t bytes = (uint32_t)((h.x & 0xffff) + 4 * (h.x >> 16)) * 8u;
+            mbar_arrive_expect_tx(&sm.bar, bytes);
+            bulk_g2s(is_sp ? ent_sp : ent_bi,
+                     is_sp ? sp.tl_pack + ti_sp * sp.entcap : bi.tl_pack + ti_bi * bi.entcap, bytes, &sm.bar);
+        }
+    }
+    if (n_copies == 0 && tid == 0) mbar_arrive_expect_tx(&sm.bar, 0);
+
+    // ---- per-pixel data (thread = pixel) ----
     float t[MP];
     {
         const float *Ub = U + (size_t)b * M * N + pix;
 #pragma unroll
-        for (int k = 0; k < MP; k++) t[k] = (in && k < M) ? Ub[(size_t)k * N] : 0.0f;
+        for (int k = 0; k < MP; k++) {
+            t[k] = (in && k < M) ? *Ub : 0.0f;
+            Ub += N;
+        }
     }
     float w_sp[3], w_bi[6];
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        w_sp[r] = in ? sp.wn[px_sp + r * strideN] : 0.0f;
-        sm.wn[r * 256 + tid] = w_sp[r];
-    }
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-        w_bi[r] = in ? bi.wn[px_bi + r * strideN] : 0.0f;
-        sm.wn[(3 + r) * 256 + tid] = w_bi[r];
-    }
     {
-        const int32_t *r_sp = sp.tl_rows + ti_sp * kMaxLocSp, *r_bi = bi.tl_rows + ti_bi * kMaxLocBi;
-        for (int i = tid; i < n_sp; i += 256) rows_sp[i] = base_sp + r_sp[i];
-        for (int i = tid; i < n_bi; i += 256) rows_bi[i] = base_bi + r_bi[i];
+        const float *p = sp.wn + px_sp;
+#pragma unroll
+        for (int r = 0; r < 3; r++, p += N) w_sp[r] = in ? *p : 0.0f;
+        p = bi.wn + px_bi;
+#pragma unroll
+        for (int r = 0; r < 6; r++, p += N) w_bi[r] = in ? *p : 0.0f;
     }
-    const uint16_t *p_sp = sp.tl_ptr + ti_sp * (kMaxLocSp + 1), *p_bi = bi.tl_ptr + ti_bi * (kMaxLocBi + 1);
-    const int ne_sp = (MODE != MODE_LAST && !fb_sp) ? p_sp[n_sp] : 0;
-    const int ne_bi = (MODE != MODE_LAST && !fb_bi) ? p_bi[n_bi] : 0;
-    __syncthreads();
-
-    // ---- phase B: stage the value rows (slice source) and pack the CSR entries (splat) ----
-    if (MODE != MODE_FIRST) {
-        const float4 *vin_sp = reinterpret_cast<const float4 *>(sp.val_in);
-        const float4 *vin_bi = reinterpret_cast<const float4 *>(bi.val_in);
-        for (int i = tid; i < n_sp * CH; i += 256) {
-            const int lv = i / CH, c = i - lv * CH;
-            vs_sp[i] = vin_sp[(size_t)rows_sp[lv] * CH + c];
-        }
-        for (int i = tid; i < n_bi * CH; i += 256) {
-            const int lv = i / CH, c = i - lv * CH;
-            vs_bi[i] = vin_bi[(size_t)rows_bi[lv] * CH + c];
-        }
-    }
-    if (MODE != MODE_LAST) {
-        const uint16_t *e_sp = sp.tl_ent + ti_sp * (256 * 3), *e_bi = bi.tl_ent + ti_bi * (256 * 6);
-        for (int i = tid; i < ne_sp; i += 256) {
-            const int en = e_sp[i];
-            const int p = en >> 3, r = en & 7;
-            sm.ent[i] = make_int2(p * (CH * 16), __float_as_int(sm.wn[r * 256 + p]));
-        }
-        for (int i = tid; i < ne_bi; i += 256) {
-            const int en = e_bi[i];
-            const int p = en >> 3, r = en & 7;
-            sm.ent[3 * 256 + i] = make_int2(p * (CH * 16), __float_as_int(sm.wn[(3 + r) * 256 + p]));
-        }
-        for (int i = tid; i <= n_sp; i += 256) sm.ptr[i] = p_sp[i];
-        for (int i = tid; i <= n_bi; i += 256) sm.ptr[kMaxLocSp + 1 + i] = p_bi[i];
-    }
-    __syncthreads();
+    mbar_wait(&sm.bar, 0);
 
     // ---- slice + update ----
     if (MODE != MODE_FIRST && in) {
@@ -318,8 +348,10 @@ k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, Til
         if (in) {
             float *Qb = Qout + (size_t)b * M * N + pix;
 #pragma unroll
-            for (int k = 0; k < MP; k++)
-                if (k < M) Qb[(size_t)k * N] = t[k];
+            for (int k = 0; k < MP; k++) {
+                if (k < M) *Qb = t[k];
+                Qb += N;
+            }
         }
         return;
     }
@@ -331,12 +363,11 @@ k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, Til
     // ---- splat ----
     float4 *vout_sp = reinterpret_cast<float4 *>(sp.val_out), *vout_bi = reinterpret_cast<float4 *>(bi.val_out);
     if (!fb_sp)
-        tile_splat_csr<MP>(vout_sp, n_sp, sm.ptr, sm.ent, rows_sp, reinterpret_cast<const unsigned char *>(qs));
+        tile_splat_csr<MP>(vout_sp, n_sp, hdr_sp, ent_sp, reinterpret_cast<const unsigned char *>(qs));
     else if (in)
         tile_splat_direct<MP, 3>(vout_sp, sp.off + px_sp, strideN, base_sp, w_sp, t);
     if (!fb_bi)
-        tile_splat_csr<MP>(vout_bi, n_bi, sm.ptr + kMaxLocSp + 1, sm.ent + 3 * 256, rows_bi,
-                           reinterpret_cast<const unsigned char *>(qs));
+        tile_splat_csr<MP>(vout_bi, n_bi, hdr_bi, ent_bi, reinterpret_cast<const unsigned char *>(qs));
     else if (in)
         tile_splat_direct<MP, 6>(vout_bi, bi.off + px_bi, strideN, base_bi, w_bi, t);
 }
@@ -452,9 +483,9 @@ static TileLat make_tile_view(const Lattice &L, const float *val_in, float *val_
     v.off = L.off;
     v.rowbase = L.rowbase;
     v.tl_nloc = L.tl_nloc;
-    v.tl_rows = L.tl_rows;
-    v.tl_ptr = L.tl_ptr;
-    v.tl_ent = L.tl_ent;
+    v.tl_hdr = L.tl_hdr;
+    v.tl_pack = L.tl_pack;
+    v.entcap = L.entcap;
     v.tl_loc = L.tl_loc;
     v.wn = L.wn;
     v.val_in = val_in;
