@@ -81,7 +81,7 @@ static int lattice_alloc(Engine *e, Lattice &L, int d, int shared) {
     L.maxloc = (d == 2) ? kMaxLocSp : kMaxLocBi;
     const size_t nt = n * e->ntiles;
     rc |= dalloc(e, &L.tl_nloc, nt);
-    L.entcap = 256 * (d + 1) + 3 * L.maxloc;
+    L.entcap = 256 * (d + 1) + 2;  // + room for the 16-byte rounding, kept even
     rc |= dalloc(e, &L.tl_hdr, nt * L.maxloc);
     rc |= dalloc(e, &L.tl_pack, nt * L.entcap);
     rc |= dalloc(e, &L.tl_loc, n * (d + 1) * L.N);
@@ -272,6 +272,7 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     e->N = H * W;
     e->sm_count = prop.multiProcessorCount;
     e->tiles_x = (W + kTileW - 1) / kTileW;
+    e->tile_w = (W + e->tiles_x - 1) / e->tiles_x;  // e.g. W=321: 11 tiles of 30 instead of 10 x 32 + a 1-pixel sliver
     e->tiles_y = (H + kTileH - 1) / kTileH;
     e->ntiles = e->tiles_x * e->tiles_y;
     int rc = 0;
@@ -519,7 +520,7 @@ int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels, float *pr
         return DSRG_E_INVALID;
     }
     if ((rc = ensure_staging(e))) return rc;
-    const int chunk = e->host_chunk > 0 ? e->host_chunk : 16;
+    const int chunk = e->host_chunk > 0 ? e->host_chunk : 8;
     const int nchunks = (B + chunk - 1) / chunk;
     while ((int)e->pipe_events.size() < 2 * nchunks) {
         cudaEvent_t ev;

@@ -56,10 +56,10 @@ struct Lattice {
     // slice run out of shared memory (see tiles.cu)
     int maxloc = 0;                // local-vertex capacity per tile; tiles beyond it use the fallback
     int32_t *tl_nloc = nullptr;    // [nimg][ntiles] distinct vertices of the tile, -1 = overflow
-    int2 *tl_hdr = nullptr;        // [nimg][ntiles][maxloc] per local vertex: (first entry | quads<<16, local row id)
-    int2 *tl_pack = nullptr;       // [nimg][ntiles][entcap] CSR entries grouped by local vertex, segments padded
-                                   // to 4: (byte offset of the pixel's Q row in the tile, weight bits)
-    int entcap = 0;                // 256*(d+1) + 3*maxloc
+    int2 *tl_hdr = nullptr;        // [nimg][ntiles][maxloc] per local vertex: (first entry | count<<16, local row id)
+    int2 *tl_pack = nullptr;       // [nimg][ntiles][entcap] CSR entries grouped by local vertex:
+                                   // (byte offset of the pixel's Q row in the tile, weight bits)
+    int entcap = 0;                // 256*(d+1) + 2
     uint16_t *tl_loc = nullptr;    // [nimg][d+1][N] local vertex index of (pixel, r)
     float *wn = nullptr;           // [nimg][d+1][N] barycentric weight * norm
     float scale[5] = {0, 0, 0, 0, 0};  // elevation scale factors (permutohedral.cpp:179-182)
@@ -112,7 +112,8 @@ struct Engine {
     float *Qcur = nullptr;  // where the current marginals live (Q0 or Q1)
     // lattice value buffers [rows][MP]
     float *spA = nullptr, *spB = nullptr, *spC = nullptr, *biA = nullptr, *biB = nullptr, *biC = nullptr;
-    int tiles_x = 0, tiles_y = 0, ntiles = 0;  // 32x8-pixel tiles
+    int tiles_x = 0, tiles_y = 0, ntiles = 0;  // tiles of tile_w x 8 pixels
+    int tile_w = 32;  // <= 32: the image width is split evenly so that no sliver tiles remain
     // 1-channel buffers for the normalisation pass
     float *nvA = nullptr, *nvB = nullptr;
     // SRG state
@@ -128,7 +129,7 @@ struct Engine {
     int32_t *st_lmap = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     std::vector<cudaEvent_t> pipe_events;
-    int host_chunk = 16;  // images per pipeline stage of the *_host entry points
+    int host_chunk = 8;   // images per pipeline stage of the *_host entry points
     int *dev_err = nullptr;  // device-side error flag
     // per-kernel event timing (off by default)
     bool prof = false;

@@ -139,7 +139,7 @@ struct TileSmem {
     static constexpr int CH = MP / 4;
     static constexpr int kRows = kMaxLocSp + kMaxLocBi;
     static constexpr int kBufF4 = (kRows * CH > 256 * CH) ? kRows * CH : 256 * CH;  // staged rows / Q alias
-    static constexpr int kEntSp = 256 * 3 + 3 * kMaxLocSp, kEntBi = 256 * 6 + 3 * kMaxLocBi;
+    static constexpr int kEntSp = 256 * 3 + 2, kEntBi = 256 * 6 + 2;
     float4 buf[kBufF4];
     int2 ent[kEntSp + kEntBi];  // CSR entries (byte offset of the pixel's Q row, weight bits)
     int2 hdr[kRows];            // per local vertex (first entry | quads << 16, global row)
@@ -186,44 +186,35 @@ __device__ __forceinline__ void tile_slice_global(const float4 *vin, const int32
     }
 }
 
-// CSR splat of one lattice: warp per local vertex, lane = (entry slot 0..3, label quad 0..MP/4-1);
-// segments are padded to multiples of four entries, so every slot runs the same trip count
+// CSR splat of both lattices: one thread per (local vertex, label quad) walks the vertex's segment
+// serially and issues ONE vector reduction; vertices are ordered by segment length (tiles.cu), so the
+// lanes of a warp run similar trip counts, and no cross-lane reduction is needed.
 template <int MP>
-__device__ __forceinline__ void tile_splat_csr(float4 *vout, int nloc, const int2 *hdr_s, const int2 *ent_s,
-                                               const unsigned char *qs_bytes) {
+__device__ __forceinline__ void tile_splat_csr(float4 *vout_sp, float4 *vout_bi, int n_sp, int n_bi,
+                                               const int2 *hdr_sp, const int2 *hdr_bi, const int2 *ent_sp,
+                                               const int2 *ent_bi, const unsigned char *qs_bytes) {
     constexpr int CH = MP / 4;
-    static_assert(4 * CH <= 32, "lane mapping");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int es = lane / CH, cq = lane - es * CH;
-    const bool act = es < 4;
-    const unsigned char *qbase = qs_bytes + cq * 16;
-    for (int lv = warp; lv < nloc; lv += 8) {
-        const int2 h = hdr_s[lv];
-        const int n4 = h.x >> 16;
-        const int2 *ep = ent_s + (h.x & 0xffff) + es;
+    const int pairs_sp = n_sp * CH, pairs = (n_sp + n_bi) * CH;
+    for (int p = threadIdx.x; p < pairs; p += 256) {
+        const bool is_sp = p < pairs_sp;
+        const int q = is_sp ? p : p - pairs_sp;
+        const int lv = q / CH, cq = q - lv * CH;
+        const int2 h = (is_sp ? hdr_sp : hdr_bi)[lv];
+        const int2 *ep = (is_sp ? ent_sp : ent_bi) + (h.x & 0xffff);
+        const int n = h.x >> 16;
+        const unsigned char *qbase = qs_bytes + cq * 16;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act) {
-#pragma unroll 2
-            for (int it = 0; it < n4; ++it, ep += 4) {
-                const int2 en = *ep;
-                const float w = __int_as_float(en.y);
-                const float4 q = *reinterpret_cast<const float4 *>(qbase + en.x);
-                a.x = fmaf(w, q.x, a.x);
-                a.y = fmaf(w, q.y, a.y);
-                a.z = fmaf(w, q.z, a.z);
-                a.w = fmaf(w, q.w, a.w);
-            }
+#pragma unroll 4
+        for (int it = 0; it < n; ++it) {
+            const int2 en = ep[it];
+            const float w = __int_as_float(en.y);
+            const float4 qv = *reinterpret_cast<const float4 *>(qbase + en.x);
+            a.x = fmaf(w, qv.x, a.x);
+            a.y = fmaf(w, qv.y, a.y);
+            a.z = fmaf(w, qv.z, a.z);
+            a.w = fmaf(w, qv.w, a.w);
         }
-        // fold the 4 entry slots: lanes cq, cq+CH, cq+2CH, cq+3CH
-        a.x += __shfl_down_sync(0xffffffffu, a.x, 2 * CH);
-        a.y += __shfl_down_sync(0xffffffffu, a.y, 2 * CH);
-        a.z += __shfl_down_sync(0xffffffffu, a.z, 2 * CH);
-        a.w += __shfl_down_sync(0xffffffffu, a.w, 2 * CH);
-        a.x += __shfl_down_sync(0xffffffffu, a.x, CH);
-        a.y += __shfl_down_sync(0xffffffffu, a.y, CH);
-        a.z += __shfl_down_sync(0xffffffffu, a.z, CH);
-        a.w += __shfl_down_sync(0xffffffffu, a.w, CH);
-        if (lane < CH) atomicAdd(vout + (size_t)h.y * CH + cq, a);
+        atomicAdd((is_sp ? vout_sp : vout_bi) + (size_t)h.y * CH + cq, a);
     }
 }
 
@@ -245,7 +236,7 @@ __device__ __forceinline__ void tile_splat_direct(float4 *vout, const int32_t *o
 template <int MP, int MODE>
 __global__ void __launch_bounds__(256, 3)
 k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
-          float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles) {
+          float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles, int tile_w) {
     constexpr int CH = MP / 4;
     constexpr int kRowBytes = MP * 4;
     using SM = TileSmem<MP>;
@@ -253,8 +244,8 @@ k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, Til
     SM &sm = *reinterpret_cast<SM *>(smem_raw);
     const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int x = tx * kTileW + (tid & 31), y = ty * kTileH + (tid >> 5);
-    const bool in = x < W && y < H;
+    const int x = tx * tile_w + (tid & 31), y = ty * kTileH + (tid >> 5);
+    const bool in = (tid & 31) < tile_w && x < W && y < H;
     const int pix = in ? y * W + x : 0;
     const int sb_sp = sp.shared ? 0 : b, sb_bi = bi.shared ? 0 : b;
     const size_t ti_sp = (size_t)sb_sp * ntiles + tile, ti_bi = (size_t)sb_bi * ntiles + tile;
@@ -288,7 +279,7 @@ k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, Til
                      kRowBytes, &sm.bar);
         }
         if (MODE != MODE_LAST && lv == (is_sp ? n_sp : n_bi) - 1) {  // the last segment tells the block's length
-            const uint32_t bytes = (uint32_t)((h.x & 0xffff) + 4 * (h.x >> 16)) * 8u;
+            const uint32_t bytes = (uint32_t)(((h.x & 0xffff) + (h.x >> 16) + 1) & ~1) * 8u;
             mbar_arrive_expect_tx(&sm.bar, bytes);
             bulk_g2s(is_sp ? ent_sp : ent_bi,
                      is_sp ? sp.tl_pack + ti_sp * sp.entcap : bi.tl_pack + ti_bi * bi.entcap, bytes, &sm.bar);
@@ -362,14 +353,10 @@ k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, Til
     __syncthreads();
     // ---- splat ----
     float4 *vout_sp = reinterpret_cast<float4 *>(sp.val_out), *vout_bi = reinterpret_cast<float4 *>(bi.val_out);
-    if (!fb_sp)
-        tile_splat_csr<MP>(vout_sp, n_sp, hdr_sp, ent_sp, reinterpret_cast<const unsigned char *>(qs));
-    else if (in)
-        tile_splat_direct<MP, 3>(vout_sp, sp.off + px_sp, strideN, base_sp, w_sp, t);
-    if (!fb_bi)
-        tile_splat_csr<MP>(vout_bi, n_bi, hdr_bi, ent_bi, reinterpret_cast<const unsigned char *>(qs));
-    else if (in)
-        tile_splat_direct<MP, 6>(vout_bi, bi.off + px_bi, strideN, base_bi, w_bi, t);
+    if (fb_sp && in) tile_splat_direct<MP, 3>(vout_sp, sp.off + px_sp, strideN, base_sp, w_sp, t);
+    if (fb_bi && in) tile_splat_direct<MP, 6>(vout_bi, bi.off + px_bi, strideN, base_bi, w_bi, t);
+    tile_splat_csr<MP>(vout_sp, vout_bi, n_sp, n_bi, hdr_sp, hdr_bi, ent_sp, ent_bi,
+                       reinterpret_cast<const unsigned char *>(qs));
 }
 
 // zero the splat targets of both lattices (row counts are device-resident)
@@ -547,15 +534,15 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
         if (it == 0) {
             DSRG_LAUNCH(e, T_MF_TILE, s,
                         (k_mf_tile<MP, MODE_FIRST><<<gt, 256, smem, s>>>(e->U, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
-                                                                         e->H, e->tiles_x, e->ntiles)));
+                                                                         e->H, e->tiles_x, e->ntiles, e->tile_w)));
         } else if (it < T) {
             DSRG_LAUNCH(e, T_MF_TILE, s,
                         (k_mf_tile<MP, MODE_MID><<<gt, 256, smem, s>>>(e->U, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
-                                                                       e->H, e->tiles_x, e->ntiles)));
+                                                                       e->H, e->tiles_x, e->ntiles, e->tile_w)));
         } else {
             DSRG_LAUNCH(e, T_MF_TILE, s,
                         (k_mf_tile<MP, MODE_LAST><<<gt, 256, smem, s>>>(e->U, e->Q0, vsp, vbi, c_sp, c_bi, M, N, e->W,
-                                                                        e->H, e->tiles_x, e->ntiles)));
+                                                                        e->H, e->tiles_x, e->ntiles, e->tile_w)));
             break;
         }
         // the old X is dead: it becomes the next (zeroed) splat target

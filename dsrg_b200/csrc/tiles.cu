@@ -6,9 +6,9 @@
 // finds them once per lattice build: per tile the distinct rows with, for each, its segment of the
 // transposed incidence (tl_hdr), per pixel the index into that list (tl_loc), and the incidence
 // itself as a CSR grouped by local vertex whose entries are already in the form the mean-field
-// kernel consumes (tl_pack: byte offset of the pixel's Q row inside the tile, weight).  Segments
-// are padded to multiples of four entries (zero weight) so that the consumer's loop has no
-// remainder and the whole entry list is one 16-byte-aligned block for a bulk copy.
+// kernel consumes (tl_pack: byte offset of the pixel's Q row inside the tile, weight); the whole
+// entry list of a tile is one 16-byte-aligned block for a bulk copy.  Local vertices are numbered
+// by decreasing segment length.
 // The symmetric normalisation is folded into the weights: wn = bary * norm (pairwise.cpp:66,79).
 #include "common.cuh"
 
@@ -18,7 +18,7 @@ template <int DP1, int MAXLOC, int MP>
 __global__ void __launch_bounds__(256)
 k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *tl_nloc, int2 *tl_hdr,
              int2 *tl_pack, uint16_t *tl_loc, float *wn, int N, int W, int H, int tiles_x, int ntiles,
-             int entcap) {
+             int entcap, int tile_w) {
     constexpr int HS = 2048;  // >= 256*DP1 distinct rows in the worst case, power of two
     static_assert(MAXLOC <= 256, "one scan element per thread");
     __shared__ int hkey[HS];
@@ -27,12 +27,14 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
     __shared__ int cnt[MAXLOC];
     __shared__ int ptr[MAXLOC + 1];
     __shared__ int wsum[8];
+    __shared__ int perm[MAXLOC];
+    __shared__ int scnt[MAXLOC];
     __shared__ int count;
 
     const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int x = tx * kTileW + (tid & 31), y = ty * kTileH + (tid >> 5);
-    const bool in = x < W && y < H;
+    const int x = tx * tile_w + (tid & 31), y = ty * kTileH + (tid >> 5);
+    const bool in = (tid & 31) < tile_w && x < W && y < H;
     const int pix = y * W + x;
     for (int i = tid; i < HS; i += 256) hkey[i] = -1;
     if (tid < MAXLOC) cnt[tid] = 0;
@@ -71,21 +73,32 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
         if (tid == 0) tl_nloc[tile] = -1;
         return;
     }
+    // order the local vertices by decreasing segment length so that the lanes of a warp of the
+    // consumer (one lane per (vertex, label quad)) walk segments of similar length
     int lv[DP1];
     if (in) {
 #pragma unroll
         for (int r = 0; r < DP1; r++) {
             lv[r] = hlv[slot[r]];
-            tl_loc[((size_t)b * DP1 + r) * N + pix] = (uint16_t)lv[r];
             atomicAdd(&cnt[lv[r]], 1);
         }
     }
     __syncthreads();
-    // exclusive scan of the PADDED segment lengths -> ptr
-    const int mycnt = tid < MAXLOC ? cnt[tid] : 0;
-    const int mypad = (mycnt + 3) & ~3;
+    const int mycnt = tid < nloc ? cnt[tid] : 0;
+    if (tid < nloc) {
+        int rank = 0;
+        for (int j = 0; j < nloc; j++) {
+            const int cj = cnt[j];
+            rank += (cj > mycnt) || (cj == mycnt && j < tid);
+        }
+        perm[tid] = rank;      // new index of local vertex `tid`
+        scnt[rank] = mycnt;    // counts in the new order
+    }
+    __syncthreads();
+    // exclusive scan of the reordered counts -> ptr
     {
-        int incl = mypad;
+        const int v = tid < nloc ? scnt[tid] : 0;
+        int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int n = __shfl_up_sync(0xffffffffu, incl, o);
@@ -96,8 +109,8 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
         int base = 0;
         for (int k = 0; k < (tid >> 5); k++) base += wsum[k];
         if (tid < MAXLOC) {
-            ptr[tid] = base + incl - mypad;
-            cnt[tid] = 0;  // reused as the fill cursor
+            ptr[tid] = base + incl - v;
+            cnt[tid] = 0;  // reused as the fill cursor (indexed by the NEW vertex index)
         }
     }
     __syncthreads();
@@ -105,15 +118,21 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
     if (in) {
 #pragma unroll
         for (int r = 0; r < DP1; r++) {
-            int pos = ptr[lv[r]] + atomicAdd(&cnt[lv[r]], 1);
+            const int nv = perm[lv[r]];
+            tl_loc[((size_t)b * DP1 + r) * N + pix] = (uint16_t)nv;
+            const int pos = ptr[nv] + atomicAdd(&cnt[nv], 1);
             pack[pos] = make_int2(tid * (MP * 4), __float_as_int(w[r]));
         }
     }
     if (tid < nloc) {
-        for (int k = mycnt; k < mypad; k++) pack[ptr[tid] + k] = make_int2(0, 0);  // zero-weight padding
-        tl_hdr[((size_t)b * ntiles + tile) * MAXLOC + tid] = make_int2(ptr[tid] | ((mypad >> 2) << 16), rows_s[tid]);
+        const int nv = perm[tid];
+        tl_hdr[((size_t)b * ntiles + tile) * MAXLOC + nv] = make_int2(ptr[nv] | (mycnt << 16), rows_s[tid]);
     }
-    if (tid == 0) tl_nloc[tile] = nloc;
+    if (tid == 0) {
+        const int total = ptr[nloc - 1] + scnt[nloc - 1];
+        if (total & 1) pack[total] = make_int2(0, 0);  // the block is bulk-copied in 16-byte units
+        tl_nloc[tile] = nloc;
+    }
 }
 
 int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s) {
@@ -122,7 +141,7 @@ int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s) {
     DSRG_LAUNCH(e, T_LAT_MISC, s,                                                                            \
                 (k_tile_build<DP1, MAXLOC, MPV><<<g, 256, 0, s>>>(L.off, L.bary, L.norm, L.tl_nloc, L.tl_hdr, \
                                                                   L.tl_pack, L.tl_loc, L.wn, L.N, e->W, e->H,  \
-                                                                  e->tiles_x, e->ntiles, L.entcap)))
+                                                                  e->tiles_x, e->ntiles, L.entcap, e->tile_w)))
 #define DSRG_TILE_BUILD_MP(MPV)                           \
     if (L.d == 2) { DSRG_TILE_BUILD(3, kMaxLocSp, MPV); } \
     else { DSRG_TILE_BUILD(6, kMaxLocBi, MPV); }

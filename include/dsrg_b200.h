@@ -74,8 +74,8 @@ typedef struct dsrg_engine dsrg_engine;
 dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M);
 void dsrg_engine_destroy(dsrg_engine *e);
 size_t dsrg_engine_device_bytes(const dsrg_engine *e); /* bytes of HBM held by the engine */
-/* The *_host full-pass entry point pipelines the batch in chunks of `images` (default 16) through
- * H2D | kernels | D2H streams; 0 restores the default. */
+/* The *_host full-pass entry point pipelines the batch in chunks of `images` (default 8) through
+ * H2D | kernels | D2H streams; 0 restores the default (8). */
 int dsrg_engine_set_host_chunk(dsrg_engine *e, int images);
 /* Kernel launches issued by this engine since the last call (bench.py's gpu_launches). */
 long long dsrg_engine_take_launch_count(dsrg_engine *e);
