@@ -68,8 +68,8 @@ __device__ __forceinline__ int hash_insert(uint64_t *keys, int32_t *hval, int32_
                           (unsigned long long)k);
             if (old == kEmptyKey) {
                 int id = atomicAdd(vcount, 1);
-                hval[s] = id;
                 vslot[id] = (int)s;
+                asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(hval + s), "r"(id) : "memory");
                 return (int)s;
             }
             if (old == k) return (int)s;
@@ -209,12 +209,20 @@ __global__ void __launch_bounds__(kThreads) k_lattice_insert(BuildArgs a) {
         // neighbouring pixels mostly share vertices: one insert per distinct key per warp
         unsigned peers = __match_any_sync(0xffffffffu, valid ? pk : (kEmptyKey - 1 - lane));
         int leader = __ffs(peers) - 1;
-        int slot = 0;
-        if (valid && (int)lane == leader) slot = hash_insert(keys, hval, vslot, vcount, a.cap, pk);
-        slot = __shfl_sync(0xffffffffu, slot, leader);
+        int id = 0;
+        if (valid && (int)lane == leader) {
+            const int slot = hash_insert(keys, hval, vslot, vcount, a.cap, pk);
+            // the slot's owner publishes the vertex id right after winning the CAS; owners of the
+            // same key always sit in other warps (one leader per key per warp), so this cannot
+            // wait on a lane of the same warp
+            do {
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(id) : "l"(hval + slot) : "memory");
+            } while (id < 0);
+        }
+        id = __shfl_sync(0xffffffffu, id, leader);
         if (real) {
             size_t at = ((size_t)b * (D + 1) + r) * a.N + i;
-            a.off[at] = slot;  // slot for now; k_lattice_finalize turns it into a row id
+            a.off[at] = id + 1;  // local row (row 0 of every image is its zero row)
             a.bary[at] = bc[r];
         }
     }
@@ -230,16 +238,6 @@ __global__ void k_rowbase(const int32_t *vcount, int32_t *rowbase, int B, int sh
             if (b < B) acc += vcount[shared ? 0 : b] + 1;
         }
     }
-}
-
-// slot -> local row id (1-based)
-__global__ void __launch_bounds__(kThreads)
-k_lattice_finalize(int32_t *off, const int32_t *hval, int N, int dp1, uint32_t cap) {
-    const int b = blockIdx.y;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)dp1 * N) return;
-    size_t at = (size_t)b * dp1 * N + t;
-    off[at] = hval[(size_t)b * cap + off[at]] + 1;
 }
 
 // Kernel 3: blur neighbours of every vertex (:305-318).  Missing neighbour -> the zero row.
@@ -288,12 +286,15 @@ k_lattice_neighbors(const uint64_t *hkeys, const int32_t *hval, const int32_t *v
 
 // Kernel 4: give the slots back (the tables stay all-empty between batches, no big memset)
 __global__ void __launch_bounds__(kThreads)
-k_lattice_cleanup(uint64_t *hkeys, const int32_t *vslot, const int32_t *vcount, uint32_t cap,
+k_lattice_cleanup(uint64_t *hkeys, int32_t *hval, const int32_t *vslot, const int32_t *vcount, uint32_t cap,
                   int capv) {
     const int b = blockIdx.y;
     const int V = vcount[b];
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x)
-        hkeys[(size_t)b * cap + vslot[(size_t)b * capv + v]] = kEmptyKey;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const size_t at = (size_t)b * cap + vslot[(size_t)b * capv + v];
+        hkeys[at] = kEmptyKey;
+        hval[at] = -1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -364,13 +365,11 @@ static int build_impl(Engine *e, Lattice &L, int nb, const uint8_t *image, cudaS
     dim3 gp(cdiv(L.N + L.P, kThreads), nb);
     DSRG_LAUNCH(e, T_LAT_INSERT, s, k_lattice_insert<D><<<gp, kThreads, 0, s>>>(a));
     DSRG_LAUNCH(e, T_LAT_MISC, s, k_rowbase<<<1, 32, 0, s>>>(L.vcount, L.rowbase, L.shared ? e->maxB : nb, L.shared));
-    dim3 gf(cdiv((long long)(D + 1) * L.N, kThreads), nb);
-    DSRG_LAUNCH(e, T_LAT_MISC, s, k_lattice_finalize<<<gf, kThreads, 0, s>>>(L.off, L.hval, L.N, D + 1, a.cap));
     dim3 gv(2 * e->sm_count, nb);
     DSRG_LAUNCH(e, T_LAT_MISC, s,
                 k_lattice_neighbors<D><<<gv, kThreads, 0, s>>>(L.hkeys, L.hval, L.vslot, L.vcount, L.rowbase,
                                                                L.nbr, L.nbr_stride, a.cap, L.capv, L.shared));
-    DSRG_LAUNCH(e, T_LAT_MISC, s, k_lattice_cleanup<<<gv, kThreads, 0, s>>>(L.hkeys, L.vslot, L.vcount, a.cap, L.capv));
+    DSRG_LAUNCH(e, T_LAT_MISC, s, k_lattice_cleanup<<<gv, kThreads, 0, s>>>(L.hkeys, L.hval, L.vslot, L.vcount, a.cap, L.capv));
     return DSRG_OK;
 }
 

@@ -235,7 +235,7 @@ __device__ __forceinline__ void tile_splat_direct(float4 *vout, const int32_t *o
 
 template <int MP, int MODE>
 __global__ void __launch_bounds__(256, 3)
-k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
+k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
           float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles, int tile_w) {
     constexpr int CH = MP / 4;
     constexpr int kRowBytes = MP * 4;
@@ -290,10 +290,21 @@ k_mf_tile(const float *__restrict__ U, float *__restrict__ Qout, TileLat sp, Til
     // ---- per-pixel data (thread = pixel) ----
     float t[MP];
     {
-        const float *Ub = U + (size_t)b * M * N + pix;
+        // U is either the engine's planar copy or, for NCHW callers, the caller's buffer itself;
+        // the reference's in-place clamp (pylayers.py:312) is then applied on the fly and written
+        // back once, by the first iteration
+        const size_t ub = (size_t)b * M * N + pix;
+        const float *Ub = U + ub;
 #pragma unroll
         for (int k = 0; k < MP; k++) {
-            t[k] = (in && k < M) ? *Ub : 0.0f;
+            float v = (in && k < M) ? *Ub : 0.0f;
+            if (MODE == MODE_FIRST) {  // later iterations read the values this one wrote back
+                if (clamp && in && k < M && v < kMinProb) {
+                    v = kMinProb;
+                    U_rw[ub + (size_t)k * N] = v;
+                }
+            }
+            t[k] = v;
             Ub += N;
         }
     }
@@ -505,9 +516,16 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
     const int M = e->M, N = e->N;
     dim3 gp(cdiv(N, kThreads), B);
     const int T = p.n_iters;
-    DSRG_LAUNCH(e, T_MF_INIT, s,
-                k_mf_init<MP><<<gp, kThreads, 0, s>>>(unary, unary_rw, layout, clamp ? 1 : 0, e->U,
-                                                      T == 0 ? e->Q0 : nullptr, M, N));
+    // planar (NCHW) callers are read in place by the tile kernel; NHWC callers (and T == 0) go
+    // through the layout-converting init kernel
+    const bool direct = (layout == DSRG_LAYOUT_NCHW) && T > 0;
+    const float *Usrc = direct ? unary : e->U;
+    float *Urw = direct ? unary_rw : nullptr;
+    const int tclamp = (direct && clamp) ? 1 : 0;
+    if (!direct)
+        DSRG_LAUNCH(e, T_MF_INIT, s,
+                    k_mf_init<MP><<<gp, kThreads, 0, s>>>(unary, unary_rw, layout, clamp ? 1 : 0, e->U,
+                                                          T == 0 ? e->Q0 : nullptr, M, N));
     e->Qcur = e->Q0;
     if (T == 0) return DSRG_OK;
     const float alpha_sp = 1.0f / (1 + powf(2, -e->sp.d));  // permutohedral.cpp:571
@@ -533,15 +551,15 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
         TileLat vsp = make_tile_view(e->sp, spX, spY), vbi = make_tile_view(e->bi, biX, biY);
         if (it == 0) {
             DSRG_LAUNCH(e, T_MF_TILE, s,
-                        (k_mf_tile<MP, MODE_FIRST><<<gt, 256, smem, s>>>(e->U, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
+                        (k_mf_tile<MP, MODE_FIRST><<<gt, 256, smem, s>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
                                                                          e->H, e->tiles_x, e->ntiles, e->tile_w)));
         } else if (it < T) {
             DSRG_LAUNCH(e, T_MF_TILE, s,
-                        (k_mf_tile<MP, MODE_MID><<<gt, 256, smem, s>>>(e->U, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
+                        (k_mf_tile<MP, MODE_MID><<<gt, 256, smem, s>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
                                                                        e->H, e->tiles_x, e->ntiles, e->tile_w)));
         } else {
             DSRG_LAUNCH(e, T_MF_TILE, s,
-                        (k_mf_tile<MP, MODE_LAST><<<gt, 256, smem, s>>>(e->U, e->Q0, vsp, vbi, c_sp, c_bi, M, N, e->W,
+                        (k_mf_tile<MP, MODE_LAST><<<gt, 256, smem, s>>>(Usrc, Urw, tclamp, e->Q0, vsp, vbi, c_sp, c_bi, M, N, e->W,
                                                                         e->H, e->tiles_x, e->ntiles, e->tile_w)));
             break;
         }

@@ -67,6 +67,7 @@ k_srg_label(const float *labels, const float *probs, const float *cues, double t
         double best = 0.0, s = 0.0;
         float nseed = 0.0f;   // np.sum(seed_c[:, x, y]) (pylayers.py:268)
         float cue_at_L = 0.0f;
+#pragma unroll 7
         for (int c = 0; c < M; c++) {
             const float cu = cb[(size_t)c * N];
             nseed += cu;
@@ -168,6 +169,7 @@ k_srg_emit(const float *cues, const uint8_t *lmap, const uint8_t *lflag, const i
     }
     const float *cb = cues + (size_t)b * M * N + i;
     float *ob = seeds_out + (size_t)b * M * N + i;
+#pragma unroll 7
     for (int c = 0; c < M; c++) ob[(size_t)c * N] = (c == grow_c) ? 1.0f : cb[(size_t)c * N];
 }
 
