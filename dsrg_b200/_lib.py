@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdsrg_b200.so")
+LIB_PATH = os.environ.get("DSRG_B200_LIB") or os.path.join(_HERE, "lib", "libdsrg_b200.so")  # env: A/B-test builds
 
 OK, E_INVALID, E_CUDA, E_KEYRANGE, E_STATE, E_NOMEM = 0, -1, -2, -3, -4, -5
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
@@ -80,7 +80,7 @@ def lib():
     if _LIB is None:
         try:  # a stale .so silently tests yesterday's kernels: rebuild when a source is newer
             from . import build as _build
-            if _build.needs_build():
+            if not os.environ.get("DSRG_B200_LIB") and _build.needs_build():
                 _build.build()
         except Exception:  # no nvcc here: fall through to whatever was prebuilt
             pass

@@ -79,7 +79,17 @@ enum KTag {
 int lattice_build(Engine *e, Lattice &L, int B, const uint8_t *image_dev, cudaStream_t s);
 // ---- tiles.cu ----
 constexpr int kTileW = 32, kTileH = 8;       // one thread per pixel, one warp per tile row
-constexpr int kMaxLocSp = 128, kMaxLocBi = 256;
+#ifndef DSRG_MAXLOC_BI
+#define DSRG_MAXLOC_BI 192
+#endif
+#ifndef DSRG_TILE_CTAS
+#define DSRG_TILE_CTAS 4
+#endif
+#ifndef DSRG_SPLAT_UNROLL
+#define DSRG_SPLAT_UNROLL 8
+#endif
+constexpr int kMaxLocSp = 128, kMaxLocBi = DSRG_MAXLOC_BI;
+constexpr int kSplatUnroll = DSRG_SPLAT_UNROLL;
 int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s);
 // ---- meanfield.cu ----
 int meanfield_run(Engine *e, int B, const float *unary, int unary_layout, bool clamp_inplace,

@@ -153,7 +153,7 @@ __device__ __forceinline__ void tile_slice_smem(const float4 *vs, const uint16_t
     constexpr int CH = MP / 4;
 #pragma unroll
     for (int r = 0; r < DP1; r++) {
-        const float4 *row = vs + (int)loc[r * stride] * CH;
+        const float4 *row = vs + (int)__ldg(loc + r * stride) * CH;
         const float wr = coef * w[r];
 #pragma unroll
         for (int c = 0; c < CH; c++) {
@@ -204,7 +204,7 @@ __device__ __forceinline__ void tile_splat_csr(float4 *vout_sp, float4 *vout_bi,
         const int n = h.x >> 16;
         const unsigned char *qbase = qs_bytes + cq * 16;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll kSplatUnroll
         for (int it = 0; it < n; ++it) {
             const int2 en = ep[it];
             const float w = __int_as_float(en.y);
@@ -234,7 +234,7 @@ __device__ __forceinline__ void tile_splat_direct(float4 *vout, const int32_t *o
 }
 
 template <int MP, int MODE>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, DSRG_TILE_CTAS)
 k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
           float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles, int tile_w) {
     constexpr int CH = MP / 4;
@@ -297,7 +297,8 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
         const float *Ub = U + ub;
 #pragma unroll
         for (int k = 0; k < MP; k++) {
-            float v = (in && k < M) ? *Ub : 0.0f;
+            float v = 0.0f;
+            if (in && k < M) v = (MODE == MODE_FIRST) ? *Ub : __ldg(Ub);  // read-only path once nothing writes U
             if (MODE == MODE_FIRST) {  // later iterations read the values this one wrote back
                 if (clamp && in && k < M && v < kMinProb) {
                     v = kMinProb;
@@ -312,10 +313,10 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     {
         const float *p = sp.wn + px_sp;
 #pragma unroll
-        for (int r = 0; r < 3; r++, p += N) w_sp[r] = in ? *p : 0.0f;
+        for (int r = 0; r < 3; r++, p += N) w_sp[r] = in ? __ldg(p) : 0.0f;
         p = bi.wn + px_bi;
 #pragma unroll
-        for (int r = 0; r < 6; r++, p += N) w_bi[r] = in ? *p : 0.0f;
+        for (int r = 0; r < 6; r++, p += N) w_bi[r] = in ? __ldg(p) : 0.0f;
     }
     mbar_wait(&sm.bar, 0);
 
