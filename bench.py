@@ -207,7 +207,7 @@ def run_reference(args, rank, world):
                    "images_per_step": n},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), flush=True)
 
 
 # --------------------------------------------------------------------------------------------
@@ -223,6 +223,7 @@ def run_b200(args, rank, local_rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     H, W, B, what = WORKLOADS[args.workload]
     if args.batch:
@@ -370,7 +371,7 @@ def run_b200(args, rank, local_rank, world):
                        "parallelism": "dp%d (images shard, no data-path collective)" % world},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "kernels": kernels, "cpu_baseline": cpu_baseline,
-        }))
+        }), flush=True)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -194,11 +194,16 @@ __device__ __forceinline__ void tile_splat_csr(float4 *vout_sp, float4 *vout_bi,
                                                const int2 *hdr_sp, const int2 *hdr_bi, const int2 *ent_sp,
                                                const int2 *ent_bi, const unsigned char *qs_bytes) {
     constexpr int CH = MP / 4;
-    const int pairs_sp = n_sp * CH, pairs = (n_sp + n_bi) * CH;
+    // 8 lanes per vertex (CH of them active): every quarter-warp of an LDS.128 then reads ONE pixel
+    // row (contiguous 96 B), which is bank-conflict free; measured 3 % faster than packing CH lanes
+    constexpr int LPV = 8;
+    static_assert(CH <= LPV, "lane mapping");
+    const int pairs_sp = n_sp * LPV, pairs = (n_sp + n_bi) * LPV;
     for (int p = threadIdx.x; p < pairs; p += 256) {
         const bool is_sp = p < pairs_sp;
         const int q = is_sp ? p : p - pairs_sp;
-        const int lv = q / CH, cq = q - lv * CH;
+        const int lv = q / LPV, cq = q - lv * LPV;
+        if (cq >= CH) continue;
         const int2 h = (is_sp ? hdr_sp : hdr_bi)[lv];
         const int2 *ep = (is_sp ? ent_sp : ent_bi) + (h.x & 0xffff);
         const int n = h.x >> 16;

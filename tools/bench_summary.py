@@ -1,5 +1,5 @@
 import json, sys
-d = json.load(open(sys.argv[1]))
+d = [json.loads(l[l.index("{"):]) for l in open(sys.argv[1]) if "{" in l and "metric" in l][-1]
 print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches")}, "e2e", d["e2e"]["value"] if d.get("e2e") else None, d["clocks"])
 r = d["roofline"]; print({k: r[k] for k in ("kernel", "achieved", "frac", "avg_launch_ms", "share_of_step", "step_frac")})
 for k, v in d["kernels"].items():
