@@ -41,6 +41,7 @@ SIGNATURES = {
     "dsrg_engine_destroy": (None, [_vp]),
     "dsrg_engine_device_bytes": (_sz, [_vp]),
     "dsrg_engine_set_host_chunk": (_i, [_vp, _i]),
+    "dsrg_engine_set_lanes": (_i, [_vp, _i]),
     "dsrg_engine_take_launch_count": (_ll, [_vp]),
     "dsrg_crf_batch_dev": (_i, [_vp, _i, _vp, _i, _vp, _pp, _vp, _i, _vp]),
     "dsrg_crf_batch_host": (_i, [_vp, _i, _vp, _i, _vp, _pp, _vp, _i]),

@@ -84,6 +84,9 @@ class Engine(object):
     def set_host_chunk(self, images):
         check(self._L.dsrg_engine_set_host_chunk(self.h, int(images)))
 
+    def set_lanes(self, lanes):
+        check(self._L.dsrg_engine_set_lanes(self.h, int(lanes)))
+
     def take_launch_count(self):
         return int(self._L.dsrg_engine_take_launch_count(self.h))
 

@@ -303,6 +303,10 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     if (!rc && cudaMemset(e->dev_err, 0, sizeof(int)) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaStreamCreateWithFlags(&e->in_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
+    if (!rc && cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
+    if (!rc && cudaEventCreateWithFlags(&e->fork_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
+    if (!rc && cudaEventCreateWithFlags(&e->join_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
+    if (const char *ev = getenv("DSRG_B200_LANES")) e->lanes = atoi(ev);
     if (!rc && cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
     if (rc) {
         dsrg_engine_destroy((dsrg_engine *)e);
@@ -325,6 +329,9 @@ void dsrg_engine_destroy(dsrg_engine *h) {
     for (void *p : ptrs) cudaFree(p);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->in_stream) cudaStreamDestroy(e->in_stream);
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    if (e->fork_event) cudaEventDestroy(e->fork_event);
+    if (e->join_event) cudaEventDestroy(e->join_event);
     if (e->out_stream) cudaStreamDestroy(e->out_stream);
     for (auto ev : e->pipe_events) cudaEventDestroy(ev);
     for (auto &r : e->prof_recs) {
@@ -358,6 +365,13 @@ int dsrg_engine_set_host_chunk(dsrg_engine *h, int images) {
     Engine *e = (Engine *)h;
     if (!e || images < 0) return DSRG_E_INVALID;
     e->host_chunk = images;
+    return DSRG_OK;
+}
+
+int dsrg_engine_set_lanes(dsrg_engine *h, int lanes) {
+    Engine *e = (Engine *)h;
+    if (!e || lanes < 1 || lanes > 2) return DSRG_E_INVALID;
+    e->lanes = lanes;
     return DSRG_OK;
 }
 

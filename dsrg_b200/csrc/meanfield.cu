@@ -241,13 +241,13 @@ __device__ __forceinline__ void tile_splat_direct(float4 *vout, const int32_t *o
 template <int MP, int MODE>
 __global__ void __launch_bounds__(256, DSRG_TILE_CTAS)
 k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
-          float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles, int tile_w) {
+          float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles, int tile_w, int b0) {
     constexpr int CH = MP / 4;
     constexpr int kRowBytes = MP * 4;
     using SM = TileSmem<MP>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM &sm = *reinterpret_cast<SM *>(smem_raw);
-    const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int tile = blockIdx.x, b = b0 + blockIdx.y, tid = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int x = tx * tile_w + (tid & 31), y = ty * kTileH + (tid >> 5);
     const bool in = (tid & 31) < tile_w && x < W && y < H;
@@ -376,34 +376,36 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
                        reinterpret_cast<const unsigned char *>(qs));
 }
 
-// zero the splat targets of both lattices (row counts are device-resident)
+// zero the splat targets of both lattices for images [b0, b0+nb) (row counts are device-resident)
 template <int MP>
 __global__ void __launch_bounds__(kThreads)
-k_mf_zero(float4 *a, const int32_t *rowbase_a, float4 *c, const int32_t *rowbase_c, int B) {
+k_mf_zero(float4 *a, const int32_t *rowbase_a, float4 *c, const int32_t *rowbase_c, int b0, int nb) {
     constexpr int CH = MP / 4;
-    const long long na = (long long)rowbase_a[B] * CH, nc = (long long)rowbase_c[B] * CH;
+    const long long a0 = (long long)rowbase_a[b0] * CH, c0 = (long long)rowbase_c[b0] * CH;
+    const long long na = (long long)rowbase_a[b0 + nb] * CH - a0, nc = (long long)rowbase_c[b0 + nb] * CH - c0;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < na + nc;
          t += (long long)gridDim.x * blockDim.x) {
-        if (t < na) a[t] = z; else c[t - na] = z;
+        if (t < na) a[a0 + t] = z; else c[c0 + t - na] = z;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // blur along one lattice axis: new = old + 0.5 (old[n1] + old[n2])  (permutohedral.cpp:556-569)
-// one thread per (row, float4 chunk)
+// one thread per (row, float4 chunk), rows of images [b0, b0+nb)
 // ---------------------------------------------------------------------------------------------
 template <int MP>
 __global__ void __launch_bounds__(kThreads)
-k_mf_blur(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase, int B, int shared) {
+k_mf_blur(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase, int b0, int nb, int shared) {
     constexpr int CH = MP / 4;
-    const long long rows = rowbase[B];
+    const long long r0 = rowbase[b0], rows = rowbase[b0 + nb] - r0;
     const int rows_img = shared ? rowbase[1] : 0;
     const long long total = rows * CH;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
-        const long long g = t / CH;
-        const int c = (int)(t - g * CH);
+        const long long lg = t / CH;
+        const int c = (int)(t - lg * CH);
+        const long long g = r0 + lg;
         long long n1, n2;
         if (shared) {
             const long long img0 = (g / rows_img) * rows_img;
@@ -498,16 +500,16 @@ static TileLat make_tile_view(const Lattice &L, const float *val_in, float *val_
     return v;
 }
 
-// blur `buf` (just splatted) along all d+1 axes, ping-ponging with `tmp`; returns where the
-// result lives
+// blur `buf` (just splatted) along all d+1 axes for images [b0, b0+nb), ping-ponging with `tmp`;
+// returns where the result lives
 template <int MP>
-static float *blur_all(Engine *e, const Lattice &L, float *buf, float *tmp, int B, int tag, cudaStream_t s) {
+static float *blur_all(Engine *e, const Lattice &L, float *buf, float *tmp, int b0, int nb, int tag, int grid,
+                       cudaStream_t s) {
     float *src = buf, *dst = tmp;
-    const int grid = 8 * e->sm_count;
     for (int j = 0; j <= L.d; j++) {
         DSRG_LAUNCH(e, tag, s,
                     k_mf_blur<MP><<<grid, kThreads, 0, s>>>((const float4 *)src, (float4 *)dst,
-                                                            L.nbr + (size_t)j * L.nbr_stride, L.rowbase, B,
+                                                            L.nbr + (size_t)j * L.nbr_stride, L.rowbase, b0, nb,
                                                             L.shared));
         float *t = src;
         src = dst;
@@ -545,39 +547,63 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
         DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[0] = true;
     }
-    dim3 gt(e->ntiles, B);
-    const int zgrid = 8 * e->sm_count;
+    // Images are independent, so the batch runs as two half-batches on two streams: while one half
+    // is in its (DRAM-latency-bound) blur passes the other is in the (shared-memory-bound) tile
+    // kernel, and the two kinds of kernel overlap on the SMs.
+    const int nlanes = (e->lanes > 1 && B >= 8) ? 2 : 1;
+    cudaStream_t ls[2] = {s, e->aux_stream};
+    const int lb0[2] = {0, B / nlanes}, lnb[2] = {B / nlanes, B - B / nlanes};
+    const int lnb1[2] = {nlanes == 1 ? B : lnb[0], lnb[1]};
+    if (nlanes == 2) {
+        DSRG_CUDA_TRY(cudaEventRecord(e->fork_event, s));
+        DSRG_CUDA_TRY(cudaStreamWaitEvent(e->aux_stream, e->fork_event, 0));
+    }
+    const int bgrid = (8 * e->sm_count) / nlanes;
     // three value buffers per lattice: X = blurred values being sliced, Y = zeroed splat target,
-    // Z = blur scratch
+    // Z = blur scratch (the lanes use disjoint row ranges of the same buffers)
     float *spX = e->spA, *spY = e->spB, *spZ = e->spC;
     float *biX = e->biA, *biY = e->biB, *biZ = e->biC;
-    DSRG_LAUNCH(e, T_MF_ZERO, s,
-                k_mf_zero<MP><<<zgrid, kThreads, 0, s>>>((float4 *)spY, e->sp.rowbase, (float4 *)biY, e->bi.rowbase, B));
+    for (int l = 0; l < nlanes; l++)
+        DSRG_LAUNCH(e, T_MF_ZERO, ls[l],
+                    k_mf_zero<MP><<<bgrid, kThreads, 0, ls[l]>>>((float4 *)spY, e->sp.rowbase, (float4 *)biY,
+                                                                   e->bi.rowbase, lb0[l], lnb1[l]));
     for (int it = 0; it <= T; it++) {
         TileLat vsp = make_tile_view(e->sp, spX, spY), vbi = make_tile_view(e->bi, biX, biY);
-        if (it == 0) {
-            DSRG_LAUNCH(e, T_MF_TILE, s,
-                        (k_mf_tile<MP, MODE_FIRST><<<gt, 256, smem, s>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
-                                                                         e->H, e->tiles_x, e->ntiles, e->tile_w)));
-        } else if (it < T) {
-            DSRG_LAUNCH(e, T_MF_TILE, s,
-                        (k_mf_tile<MP, MODE_MID><<<gt, 256, smem, s>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M, N, e->W,
-                                                                       e->H, e->tiles_x, e->ntiles, e->tile_w)));
-        } else {
-            DSRG_LAUNCH(e, T_MF_TILE, s,
-                        (k_mf_tile<MP, MODE_LAST><<<gt, 256, smem, s>>>(Usrc, Urw, tclamp, e->Q0, vsp, vbi, c_sp, c_bi, M, N, e->W,
-                                                                        e->H, e->tiles_x, e->ntiles, e->tile_w)));
-            break;
+        float *sp_res = nullptr, *bi_res = nullptr;
+        for (int l = 0; l < nlanes; l++) {
+            cudaStream_t st = ls[l];
+            const int b0 = lb0[l], nb = lnb1[l];
+            dim3 gt(e->ntiles, nb);
+            if (it == 0) {
+                DSRG_LAUNCH(e, T_MF_TILE, st,
+                            (k_mf_tile<MP, MODE_FIRST><<<gt, 256, smem, st>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M,
+                                                                              N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));
+            } else if (it < T) {
+                DSRG_LAUNCH(e, T_MF_TILE, st,
+                            (k_mf_tile<MP, MODE_MID><<<gt, 256, smem, st>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M,
+                                                                            N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));
+            } else {
+                DSRG_LAUNCH(e, T_MF_TILE, st,
+                            (k_mf_tile<MP, MODE_LAST><<<gt, 256, smem, st>>>(Usrc, Urw, tclamp, e->Q0, vsp, vbi, c_sp, c_bi, M,
+                                                                             N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));
+                continue;
+            }
+            // the old X is dead: it becomes the next (zeroed) splat target
+            DSRG_LAUNCH(e, T_MF_ZERO, st,
+                        k_mf_zero<MP><<<bgrid, kThreads, 0, st>>>((float4 *)spX, e->sp.rowbase, (float4 *)biX,
+                                                                    e->bi.rowbase, b0, nb));
+            sp_res = blur_all<MP>(e, e->sp, spY, spZ, b0, nb, T_MF_BLUR_SP, bgrid, st);
+            bi_res = blur_all<MP>(e, e->bi, biY, biZ, b0, nb, T_MF_BLUR_BI, bgrid, st);
         }
-        // the old X is dead: it becomes the next (zeroed) splat target
-        DSRG_LAUNCH(e, T_MF_ZERO, s,
-                    k_mf_zero<MP><<<zgrid, kThreads, 0, s>>>((float4 *)spX, e->sp.rowbase, (float4 *)biX, e->bi.rowbase, B));
-        float *sp_res = blur_all<MP>(e, e->sp, spY, spZ, B, T_MF_BLUR_SP, s);
-        float *bi_res = blur_all<MP>(e, e->bi, biY, biZ, B, T_MF_BLUR_BI, s);
+        if (it == T) break;
         float *sp_other = (sp_res == spY) ? spZ : spY, *bi_other = (bi_res == biY) ? biZ : biY;
         float *nspY = spX, *nbiY = biX;
         spX = sp_res; spY = nspY; spZ = sp_other;
         biX = bi_res; biY = nbiY; biZ = bi_other;
+    }
+    if (nlanes == 2) {
+        DSRG_CUDA_TRY(cudaEventRecord(e->join_event, e->aux_stream));
+        DSRG_CUDA_TRY(cudaStreamWaitEvent(s, e->join_event, 0));
     }
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;

@@ -77,6 +77,10 @@ size_t dsrg_engine_device_bytes(const dsrg_engine *e); /* bytes of HBM held by t
 /* The *_host full-pass entry point pipelines the batch in chunks of `images` (default 8) through
  * H2D | kernels | D2H streams; 0 restores the default (8). */
 int dsrg_engine_set_host_chunk(dsrg_engine *e, int images);
+/* Experimental: run the mean-field loop as `lanes` (1 or 2, default 1) half-batches on separate
+ * streams so that the DRAM-latency-bound blur passes of one half overlap the shared-memory-bound tile
+ * kernel of the other (measured on B200: +1 %, so it is off by default). */
+int dsrg_engine_set_lanes(dsrg_engine *e, int lanes);
 /* Kernel launches issued by this engine since the last call (bench.py's gpu_launches). */
 long long dsrg_engine_take_launch_count(dsrg_engine *e);
 
