@@ -129,9 +129,12 @@ class ClockSampler(object):
         return out
 
 
+IMAGE_VARIANT = "smooth"
+
+
 def synth_batch(H, W, B, unique=8):
     from dsrg_b200 import synth
-    return synth.make_batch(B, H, W, cues="cam", image="smooth", unique=unique)
+    return synth.make_batch(B, H, W, cues="cam", image=IMAGE_VARIANT, unique=unique)
 
 
 # --------------------------------------------------------------------------------------------
@@ -366,7 +369,7 @@ def run_b200(args, rank, local_rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "what": what, "H": H, "W": W, "labels": M, "batch_per_gpu": B,
                        "global_batch": B * world, "mean_field_iters": T_ITERS, "sigma": "bilateral 80/13, spatial 3",
-                       "thresholds": [TH1, TH2], "images": "smooth, cam-like cues, 8 distinct images repeated",
+                       "thresholds": [TH1, TH2], "images": "%s, cam-like cues, 8 distinct images repeated" % IMAGE_VARIANT,
                        "l2": "inputs larger than L2 (%.0f MB of probs+cues per step)" % (2 * 4 * M * N * B / 1e6),
                        "parallelism": "dp%d (images shard, no data-path collective)" % world},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
@@ -386,7 +389,12 @@ def main():
     ap.add_argument("--workload", default="dsrg321", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--images", default="smooth", choices=["smooth", "noise"],
+                    help="synthetic image variant: smooth (headline) or uniform noise (worst case: every tile "
+                         "overflows the shared-memory path)")
     args = ap.parse_args()
+    global IMAGE_VARIANT
+    IMAGE_VARIANT = args.images
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -306,7 +306,8 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     if (!rc && cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaEventCreateWithFlags(&e->fork_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaEventCreateWithFlags(&e->join_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
-    if (const char *ev = getenv("DSRG_B200_LANES")) e->lanes = atoi(ev);
+    if (const char *ev = getenv("DSRG_B200_LANES")) e->lanes = atoi(ev) == 2 ? 2 : 1;
+    if (const char *ev = getenv("DSRG_B200_HOST_CHUNK")) e->host_chunk = atoi(ev) > 0 ? atoi(ev) : e->host_chunk;
     if (!rc && cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
     if (rc) {
         dsrg_engine_destroy((dsrg_engine *)e);

@@ -36,6 +36,8 @@ def test_crf_golden_cases_object_api(torch_cuda, name):
     (64, 48, 1.0, "smooth", "logp"),    # test-time shape (test-ms.py:106: unary=log p)
     (50, 75, 1.0, "noise", "logp"),
     (97, 113, 1.0, "smooth", "logp"),
+    (321, 321, 1.0, "smooth", "p"),     # BASELINE.json config 3 shape (batch shortened to 3)
+    (161, 200, 1.0, "noise", "p"),      # noise image: tiles overflow the shared-memory path -> direct path
     (5, 3, 1.0, "noise", "p"),          # tiny, N % 4 == 3 (one phantom lane)
     (4, 4, 12.0, "smooth", "p"),        # N % 4 == 0 (no phantom lanes)
     (1, 1, 1.0, "noise", "logp"),

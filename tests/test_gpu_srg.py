@@ -81,13 +81,14 @@ def test_srg_host_entry_and_renorm_mode(torch_cuda):
     eng.close()
 
 
-@pytest.mark.parametrize("H,W,sf,img", [(41, 41, 12.0, "smooth"), (64, 80, 12.0, "noise"), (96, 96, 1.0, "smooth")])
+@pytest.mark.parametrize("H,W,sf,img", [(41, 41, 12.0, "smooth"), (64, 80, 12.0, "noise"), (96, 96, 1.0, "smooth"),
+                                        (513, 513, 1.0, "smooth")])   # BASELINE.json config 4 shape
 def test_dsrg_forward_fused_pass(torch_cuda, H, W, sf, img):
     """DSRGLayer.forward body: CRF marginals within 1e-4 of the oracle's refinement; seeds bit-exact
     w.r.t. the reference SRG applied to THIS call's marginals (the CRF->SRG seam, SURVEY hard part 3);
     the probs buffer is clamped in place like the reference's blob (pylayers.py:312)."""
     torch = torch_cuda
-    B, M = 3, 21
+    B, M = (3, 21) if H < 500 else (2, 21)
     batch = synth.make_batch(B, H, W, cues="cam", image=img, start=60)
     probs = batch["probs"].copy()
     probs[0, 2, :3, :3] = 1e-7
