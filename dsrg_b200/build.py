@@ -12,9 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdsrg_b200.so")
-SOURCES = ["api.cu", "lattice.cu", "tiles.cu", "meanfield.cu", "srg.cu", "loss.cu"]
+SOURCES = ["api.cu", "lattice.cu", "tiles.cu", "meanfield.cu", "srg.cu", "loss.cu", "wire.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--fmad=true"]
+              "-Xcompiler", "-fPIC,-fopenmp", "--fmad=true"]
 
 
 def _nvcc():
@@ -55,7 +55,8 @@ def build(force=False, verbose=False, defines=(), out=None):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp",
+                                                  "-lgomp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

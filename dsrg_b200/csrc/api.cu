@@ -109,7 +109,7 @@ static void lattice_free(Lattice &L) {
     cudaFree(L.wn);
 }
 
-static int check_device_flag(Engine *e, cudaStream_t s) {
+int check_device_flag(Engine *e, cudaStream_t s) {
     int flag = 0;
     DSRG_CUDA_TRY(cudaMemcpyAsync(&flag, e->dev_err, sizeof(int), cudaMemcpyDeviceToHost, s));
     DSRG_CUDA_TRY(cudaStreamSynchronize(s));
@@ -154,7 +154,7 @@ static int prepare_lattices(Engine *e, int B, const uint8_t *image, const dsrg_c
     return lattice_build(e, e->bi, B, image, s);
 }
 
-static int check_batch(Engine *e, int B) {
+int check_batch(Engine *e, int B) {
     if (!e) {
         set_error("engine is NULL");
         return DSRG_E_INVALID;
@@ -182,7 +182,7 @@ static int crf_core(Engine *e, int B, const float *unary, int layout, bool clamp
     return meanfield_run(e, B, unary, layout, clamp, unary_rw, *p, s);
 }
 
-static int ensure_staging(Engine *e) {
+int ensure_staging(Engine *e) {
     if (e->st_unary) return DSRG_OK;
     const size_t n = (size_t)e->maxB * e->M * e->N;
     int rc = 0;
@@ -307,6 +307,7 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     if (!rc && cudaEventCreateWithFlags(&e->fork_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaEventCreateWithFlags(&e->join_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
     if (const char *ev = getenv("DSRG_B200_LANES")) e->lanes = atoi(ev) == 2 ? 2 : 1;
+    if (const char *ev = getenv("DSRG_B200_WIRE")) e->wire_compress = atoi(ev) != 0;
     if (const char *ev = getenv("DSRG_B200_HOST_CHUNK")) e->host_chunk = atoi(ev) > 0 ? atoi(ev) : e->host_chunk;
     if (!rc && cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
     if (rc) {
@@ -335,6 +336,7 @@ void dsrg_engine_destroy(dsrg_engine *h) {
     if (e->join_event) cudaEventDestroy(e->join_event);
     if (e->out_stream) cudaStreamDestroy(e->out_stream);
     for (auto ev : e->pipe_events) cudaEventDestroy(ev);
+    wire_free(e);
     for (auto &r : e->prof_recs) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
@@ -356,7 +358,7 @@ long long dsrg_engine_take_launch_count(dsrg_engine *h) {
 static const char *kTagNames[T_COUNT] = {
     "lattice_insert", "lattice_misc", "lattice_norm", "mf_init", "mf_zero", "mf_blur_spatial",
     "mf_blur_bilateral", "mf_tile", "mf_export", "srg_label", "srg_merge", "srg_flag", "srg_emit",
-    "seedloss"};
+    "seedloss", "wire_bits"};
 
 int dsrg_profile_tag_count(void) { return T_COUNT; }
 
@@ -520,58 +522,6 @@ int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *pro
     if (crf_out && (rc = meanfield_export(e, B, crf_out, DSRG_LAYOUT_NCHW, s))) return rc;
     // SRG on the raw marginals with the float64 clamp + renormalisation fused in (renorm = 1)
     return srg_run(e, B, labels, e->Qcur, cues, th1, th2, 1, seeds_out, nullptr, s);
-}
-
-// Host-buffer version of the full pass.  The batch is cut into chunks that flow through three
-// streams (H2D | kernels | D2H) so that PCIe traffic in both directions overlaps the compute of the
-// neighbouring chunks; results are identical to one big launch because images are independent.
-int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels, float *probs,
-                           const float *cues, const uint8_t *image, const dsrg_crf_params *params,
-                           double th1, double th2, float *seeds_out, float *crf_out) {
-    Engine *e = (Engine *)h;
-    int rc = check_batch(e, B);
-    if (rc) return rc;
-    if (!labels || !probs || !cues || !image || !seeds_out) {
-        set_error("NULL pointer argument");
-        return DSRG_E_INVALID;
-    }
-    if ((rc = ensure_staging(e))) return rc;
-    const int chunk = e->host_chunk > 0 ? e->host_chunk : 8;
-    const int nchunks = (B + chunk - 1) / chunk;
-    while ((int)e->pipe_events.size() < 2 * nchunks) {
-        cudaEvent_t ev;
-        DSRG_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        e->pipe_events.push_back(ev);
-    }
-    cudaStream_t s_in = e->in_stream, s = e->own_stream, s_out = e->out_stream;
-    const size_t img_elems = (size_t)e->M * e->N;
-    for (int c = 0; c < nchunks; c++) {
-        const int b0 = c * chunk, nb = (B - b0 < chunk) ? B - b0 : chunk;
-        const size_t o = (size_t)b0 * img_elems, n = (size_t)nb * img_elems;
-        DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_labels + (size_t)b0 * e->M, labels + (size_t)b0 * e->M,
-                                      (size_t)nb * e->M * sizeof(float), cudaMemcpyHostToDevice, s_in));
-        DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary + o, probs + o, n * sizeof(float), cudaMemcpyHostToDevice, s_in));
-        DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues + o, cues + o, n * sizeof(float), cudaMemcpyHostToDevice, s_in));
-        DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image + (size_t)b0 * e->N * 3, image + (size_t)b0 * e->N * 3,
-                                      (size_t)nb * e->N * 3, cudaMemcpyHostToDevice, s_in));
-        DSRG_CUDA_TRY(cudaEventRecord(e->pipe_events[2 * c], s_in));
-        DSRG_CUDA_TRY(cudaStreamWaitEvent(s, e->pipe_events[2 * c], 0));
-        rc = dsrg_dsrg_forward_dev(h, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o,
-                                   e->st_image + (size_t)b0 * e->N * 3, params, th1, th2, e->st_out + o, nullptr, s);
-        if (rc) return rc;
-        if (crf_out) {  // raw marginals of this chunk, parked in the (now consumed) cues staging area
-            if ((rc = meanfield_export(e, nb, e->st_cues + o, DSRG_LAYOUT_NCHW, s))) return rc;
-        }
-        DSRG_CUDA_TRY(cudaEventRecord(e->pipe_events[2 * c + 1], s));
-        DSRG_CUDA_TRY(cudaStreamWaitEvent(s_out, e->pipe_events[2 * c + 1], 0));
-        DSRG_CUDA_TRY(cudaMemcpyAsync(seeds_out + o, e->st_out + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-        // the reference mutates the probs blob in place (pylayers.py:312): hand the clamped values back
-        DSRG_CUDA_TRY(cudaMemcpyAsync(probs + o, e->st_unary + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-        if (crf_out)
-            DSRG_CUDA_TRY(cudaMemcpyAsync(crf_out + o, e->st_cues + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-    }
-    DSRG_CUDA_TRY(cudaStreamSynchronize(s_out));
-    return check_device_flag(e, s);
 }
 
 int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t *image,

@@ -72,7 +72,7 @@ struct Engine;
 enum KTag {
     T_LAT_INSERT = 0, T_LAT_MISC, T_LAT_NORM, T_MF_INIT, T_MF_ZERO, T_MF_BLUR_SP,
     T_MF_BLUR_BI, T_MF_TILE, T_MF_EXPORT, T_SRG_LABEL, T_SRG_MERGE, T_SRG_FLAG, T_SRG_EMIT,
-    T_LOSS, T_COUNT
+    T_LOSS, T_WIRE, T_COUNT
 };
 
 // ---- lattice.cu ----
@@ -141,7 +141,11 @@ struct Engine {
     cudaEvent_t fork_event = nullptr, join_event = nullptr;
     int lanes = 1;  // 2 = run the mean-field loop as two half-batches on two streams (measured: +1 %, off)
     std::vector<cudaEvent_t> pipe_events;
-    int host_chunk = 8;   // images per pipeline stage of the *_host entry points
+    int host_chunk = 16;  // images per (full) pipeline stage of the *_host entry points
+    // 0/1 planes travel over PCIe as bit masks (wire.cu): device + pinned host staging, [maxB][words/image]
+    uint32_t *d_cbits = nullptr, *d_sbits = nullptr, *d_mbits = nullptr;
+    uint32_t *h_cbits = nullptr, *h_sbits = nullptr, *h_mbits = nullptr;
+    int wire_compress = 1;
     int *dev_err = nullptr;  // device-side error flag
     // per-kernel event timing (off by default)
     bool prof = false;
@@ -187,6 +191,10 @@ struct LaunchScope {
 
 
 int device_alloc(Engine *e, void **p, size_t bytes);
+int check_batch(Engine *e, int B);
+int ensure_staging(Engine *e);
+int check_device_flag(Engine *e, cudaStream_t s);
+void wire_free(Engine *e);
 template <typename T>
 inline int dalloc(Engine *e, T **p, size_t count) {
     return device_alloc(e, (void **)p, count * sizeof(T));

@@ -74,8 +74,8 @@ typedef struct dsrg_engine dsrg_engine;
 dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M);
 void dsrg_engine_destroy(dsrg_engine *e);
 size_t dsrg_engine_device_bytes(const dsrg_engine *e); /* bytes of HBM held by the engine */
-/* The *_host full-pass entry point pipelines the batch in chunks of `images` (default 8) through
- * H2D | kernels | D2H streams; 0 restores the default (8). */
+/* The *_host full-pass entry point pipelines the batch in chunks of `images` (default 16, after a short ramp-up) through
+ * H2D | kernels | D2H streams; 0 restores the default. */
 int dsrg_engine_set_host_chunk(dsrg_engine *e, int images);
 /* Experimental: run the mean-field loop as `lanes` (1 or 2, default 1) half-batches on separate
  * streams so that the DRAM-latency-bound blur passes of one half overlap the shared-memory-bound tile
@@ -145,6 +145,12 @@ int dsrg_dsrg_forward_host(dsrg_engine *e, int B, const float *labels_host, floa
                            const float *cues_host, const uint8_t *image_host,
                            const dsrg_crf_params *params, double th1, double th2,
                            float *seeds_out_host, float *crf_out_host);
+
+/* Host-only helpers of the *_host wire format (0/1 planes cross PCIe as 1 bit per value, see
+ * csrc/wire.cu); exported for unit tests.  pack returns 1 if every value was exactly 0 or 1. */
+int dsrg_wire_pack_mask(const float *src_host, uint32_t *dst_bits, size_t n);
+void dsrg_wire_unpack_mask(const uint32_t *src_bits, float *dst_host, size_t n);
+void dsrg_wire_apply_clamp_mask(const uint32_t *src_bits, float *probs_host, size_t n);
 
 /*
  * CRFLayer.forward body (pylayers.py:63-88): same refinement, output log(result).
