@@ -478,33 +478,6 @@ int dsrg_srg_batch_dev(dsrg_engine *h, int B, const float *labels, const float *
                    (cudaStream_t)stream);
 }
 
-int dsrg_srg_batch_host(dsrg_engine *h, int B, const float *labels, const float *probs,
-                        const float *cues, double th1, double th2, int renorm, float *seeds_out,
-                        int32_t *label_map_out) {
-    Engine *e = (Engine *)h;
-    int rc = check_batch(e, B);
-    if (rc) return rc;
-    if (!labels || !probs || !cues || !seeds_out) {
-        set_error("NULL pointer argument");
-        return DSRG_E_INVALID;
-    }
-    if ((rc = ensure_staging(e))) return rc;
-    cudaStream_t s = e->own_stream;
-    const size_t n = (size_t)B * e->M * e->N;
-    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_labels, labels, (size_t)B * e->M * sizeof(float), cudaMemcpyHostToDevice, s));
-    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
-    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, cues, n * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = dsrg_srg_batch_dev(h, B, e->st_labels, e->st_unary, e->st_cues, th1, th2, renorm, e->st_out,
-                            label_map_out ? e->st_lmap : nullptr, s);
-    if (rc) return rc;
-    DSRG_CUDA_TRY(cudaMemcpyAsync(seeds_out, e->st_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (label_map_out)
-        DSRG_CUDA_TRY(cudaMemcpyAsync(label_map_out, e->st_lmap, (size_t)B * e->N * sizeof(int32_t),
-                                      cudaMemcpyDeviceToHost, s));
-    DSRG_CUDA_TRY(cudaStreamSynchronize(s));
-    return DSRG_OK;
-}
-
 int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *probs,
                           const float *cues, const uint8_t *image, const dsrg_crf_params *params,
                           double th1, double th2, float *seeds_out, float *crf_out, void *stream) {

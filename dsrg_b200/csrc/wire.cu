@@ -194,14 +194,14 @@ extern "C" void dsrg_wire_apply_clamp_mask(const uint32_t *src, float *probs, si
     unpack_planes(nullptr, nullptr, src, probs, n, (n + 31) / 32, 1);
 }
 
-extern "C" int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels, float *probs,
-                                      const float *cues, const uint8_t *image,
-                                      const dsrg_crf_params *params, double th1, double th2,
-                                      float *seeds_out, float *crf_out) {
+// srg_only: no CRF (probs are read-only, `renorm` as in dsrg_srg_batch_dev, optional label map out)
+static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, const float *cues,
+                     const uint8_t *image, const dsrg_crf_params *params, double th1, double th2,
+                     float *seeds_out, float *crf_out, bool srg_only, int renorm, int32_t *label_map_out) {
     Engine *e = (Engine *)h;
     int rc = check_batch(e, B);
     if (rc) return rc;
-    if (!labels || !probs || !cues || !image || !seeds_out) {
+    if (!labels || !probs || !cues || (!image && !srg_only) || !seeds_out) {
         set_error("NULL pointer argument");
         return DSRG_E_INVALID;
     }
@@ -235,8 +235,8 @@ extern "C" int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels
         const int b0 = cb0[c], nb = cnb[c];
         if (!packed[c]) return;
         const double tu = omp_get_wtime();
-        unpack_planes(e->h_sbits + (size_t)b0 * wpi, seeds_out + (size_t)b0 * img_elems, e->h_mbits + (size_t)b0 * wpi,
-                      probs + (size_t)b0 * img_elems, img_elems, wpi, nb);
+        unpack_planes(e->h_sbits + (size_t)b0 * wpi, seeds_out + (size_t)b0 * img_elems,
+                      srg_only ? nullptr : e->h_mbits + (size_t)b0 * wpi, probs + (size_t)b0 * img_elems, img_elems, wpi, nb);
         t_unpack += omp_get_wtime() - tu;
     };
     for (int c = 0; c < nchunks; c++) {
@@ -260,8 +260,9 @@ extern "C" int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels
                                           (size_t)nb * wpi * 4, cudaMemcpyHostToDevice, s_in));
         else
             DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues + o, cues + o, n * sizeof(float), cudaMemcpyHostToDevice, s_in));
-        DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image + (size_t)b0 * e->N * 3, image + (size_t)b0 * e->N * 3,
-                                      (size_t)nb * e->N * 3, cudaMemcpyHostToDevice, s_in));
+        if (!srg_only)
+            DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image + (size_t)b0 * e->N * 3, image + (size_t)b0 * e->N * 3,
+                                          (size_t)nb * e->N * 3, cudaMemcpyHostToDevice, s_in));
         DSRG_CUDA_TRY(cudaEventRecord(e->pipe_events[3 * c], s_in));
         // ---- kernels
         DSRG_CUDA_TRY(cudaStreamWaitEvent(s, e->pipe_events[3 * c], 0));
@@ -269,11 +270,16 @@ extern "C" int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels
         if (ok) {
             DSRG_LAUNCH(e, T_WIRE, s,
                         k_bits_to_float<<<gb, kThreads, 0, s>>>(e->d_cbits + (size_t)b0 * wpi, e->st_cues + o, n_img, (int)wpi));
-            DSRG_LAUNCH(e, T_WIRE, s,
-                        k_float_to_bits<1><<<gb, kThreads, 0, s>>>(e->st_unary + o, e->d_mbits + (size_t)b0 * wpi, n_img, (int)wpi));
+            if (!srg_only)
+                DSRG_LAUNCH(e, T_WIRE, s,
+                            k_float_to_bits<1><<<gb, kThreads, 0, s>>>(e->st_unary + o, e->d_mbits + (size_t)b0 * wpi, n_img, (int)wpi));
         }
-        rc = dsrg_dsrg_forward_dev(h, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o,
-                                   e->st_image + (size_t)b0 * e->N * 3, params, th1, th2, e->st_out + o, nullptr, s);
+        if (srg_only)
+            rc = dsrg_srg_batch_dev(h, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o, th1, th2,
+                                    renorm, e->st_out + o, label_map_out ? e->st_lmap + (size_t)b0 * e->N : nullptr, s);
+        else
+            rc = dsrg_dsrg_forward_dev(h, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o,
+                                       e->st_image + (size_t)b0 * e->N * 3, params, th1, th2, e->st_out + o, nullptr, s);
         if (rc) return rc;
         if (ok)
             DSRG_LAUNCH(e, T_WIRE, s,
@@ -287,13 +293,18 @@ extern "C" int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels
         if (ok) {
             DSRG_CUDA_TRY(cudaMemcpyAsync(e->h_sbits + (size_t)b0 * wpi, e->d_sbits + (size_t)b0 * wpi,
                                           (size_t)nb * wpi * 4, cudaMemcpyDeviceToHost, s_out));
-            DSRG_CUDA_TRY(cudaMemcpyAsync(e->h_mbits + (size_t)b0 * wpi, e->d_mbits + (size_t)b0 * wpi,
-                                          (size_t)nb * wpi * 4, cudaMemcpyDeviceToHost, s_out));
+            if (!srg_only)
+                DSRG_CUDA_TRY(cudaMemcpyAsync(e->h_mbits + (size_t)b0 * wpi, e->d_mbits + (size_t)b0 * wpi,
+                                              (size_t)nb * wpi * 4, cudaMemcpyDeviceToHost, s_out));
         } else {
             DSRG_CUDA_TRY(cudaMemcpyAsync(seeds_out + o, e->st_out + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
             // the reference mutates the probs blob in place (pylayers.py:312): hand the clamped values back
-            DSRG_CUDA_TRY(cudaMemcpyAsync(probs + o, e->st_unary + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+            if (!srg_only)
+                DSRG_CUDA_TRY(cudaMemcpyAsync(probs + o, e->st_unary + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         }
+        if (label_map_out)
+            DSRG_CUDA_TRY(cudaMemcpyAsync(label_map_out + (size_t)b0 * e->N, e->st_lmap + (size_t)b0 * e->N,
+                                          (size_t)nb * e->N * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
         if (crf_out)
             DSRG_CUDA_TRY(cudaMemcpyAsync(crf_out + o, e->st_cues + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         DSRG_CUDA_TRY(cudaEventRecord(e->pipe_events[3 * c + 2], s_out));
@@ -314,4 +325,19 @@ extern "C" int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels
                 1e3 * (omp_get_wtime() - t0), 1e3 * t_pack, 1e3 * t_issue, 1e3 * t_unpack, 1e3 * t_wait, host_threads(),
                 nchunks);
     return check_device_flag(e, s);
+}
+
+extern "C" int dsrg_dsrg_forward_host(dsrg_engine *h, int B, const float *labels, float *probs,
+                                      const float *cues, const uint8_t *image,
+                                      const dsrg_crf_params *params, double th1, double th2,
+                                      float *seeds_out, float *crf_out) {
+    return host_pass(h, B, labels, probs, cues, image, params, th1, th2, seeds_out, crf_out, false, 1, nullptr);
+}
+
+extern "C" int dsrg_srg_batch_host(dsrg_engine *h, int B, const float *labels, const float *probs,
+                                   const float *cues, double th1, double th2, int renorm, float *seeds_out,
+                                   int32_t *label_map_out) {
+    // probs are only read on this path (no clamp write-back), hence the const_cast
+    return host_pass(h, B, labels, const_cast<float *>(probs), cues, nullptr, nullptr, th1, th2, seeds_out, nullptr,
+                     true, renorm, label_map_out);
 }
