@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     #            H    W    B   what
+    "train41": (41, 41, 20, "crf+srg"),     # the shape the reference actually trains on (scale_factor 12)
     "dsrg321": (321, 321, 64, "crf+srg"),
     "crf321": (321, 321, 64, "crf"),
     "srg321": (321, 321, 64, "srg"),
@@ -235,7 +236,7 @@ def run_b200(args, rank, local_rank, world):
     batch = synth_batch(H, W, B)
     dev = torch.device("cuda", local_rank)
     eng = api.Engine(B, H, W, M, device=local_rank)
-    params = api.crf_params(1.0, 13, T_ITERS)
+    params = api.crf_params(12.0 if args.workload == "train41" else 1.0, 13, T_ITERS)
     d_labels = torch.from_numpy(batch["labels"]).to(dev)
     d_probs = torch.from_numpy(batch["probs"]).to(dev)
     d_cues = torch.from_numpy(batch["cues"]).to(dev)
@@ -307,8 +308,15 @@ def run_b200(args, rank, local_rank, world):
         per_launch_s = tms * 1e-3 / cnt
         ab = kernel_algorithmic_bytes(tag, N, B)
         ach = ab / per_launch_s / 1e9 if ab else 0.0
+        traffic = None   # dram__bytes_read+write per launch from the last committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(tag)
+            if tj and B and args.workload == "dsrg321":
+                traffic = tj["dram_bytes_per_launch"] * B / tj["batch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": tag, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
                     "avg_launch_ms": per_launch_s * 1e3, "share_of_step": tms / total_kernel_ms,
                     "step_algorithmic_GBs": algorithmic_bytes_per_image(what, N) * B * args.steps / (ms * 1e-3) / 1e9,
                     "step_frac": algorithmic_bytes_per_image(what, N) * B * args.steps / (ms * 1e-3) / 1e9 / peak,
@@ -368,7 +376,7 @@ def run_b200(args, rank, local_rank, world):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "what": what, "H": H, "W": W, "labels": M, "batch_per_gpu": B,
-                       "global_batch": B * world, "mean_field_iters": T_ITERS, "sigma": "bilateral 80/13, spatial 3",
+                       "global_batch": B * world, "mean_field_iters": T_ITERS, "sigma": "bilateral 80/13, spatial 3, scale_factor %g" % (12.0 if args.workload == "train41" else 1.0),
                        "thresholds": [TH1, TH2], "images": "%s, cam-like cues, 8 distinct images repeated" % IMAGE_VARIANT,
                        "l2": "inputs larger than L2 (%.0f MB of probs+cues per step)" % (2 * 4 * M * N * B / 1e6),
                        "parallelism": "dp%d (images shard, no data-path collective)" % world},
