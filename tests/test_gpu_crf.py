@@ -113,3 +113,41 @@ def test_crf_error_paths(torch_cuda):
         c.inference(1)
     assert ei.value.code == -4
     eng.close()
+
+
+@pytest.mark.parametrize("M", [2, 5, 8, 13, 32])
+def test_crf_and_srg_other_label_counts(torch_cuda, M):
+    """DenseCRF(W, H, nlabels) is generic in the label count (wrapper.pyx:23); the kernels are
+    instantiated for every multiple of 4 up to DSRG_MAX_LABELS = 32."""
+    from oracle import srg_oracle
+    torch = torch_cuda
+    H, W, B = 37, 45, 2
+    rng = np.random.RandomState(M)
+    logits = rng.randn(B, H, W, M).astype(np.float32) * 2
+    pr = np.exp(logits - logits.max(-1, keepdims=True))
+    pr /= pr.sum(-1, keepdims=True)
+    unary = np.log(np.maximum(pr, 1e-5)).astype(np.float32)
+    image = synth.make_batch(B, H, W, C=21, image="smooth", start=3)["image"]
+    want = np.stack([crf_oracle.CRF(image[b], unary[b], 10, 1.0) for b in range(B)])
+    eng = api.Engine(B, H, W, M)
+    d_un = torch.from_numpy(unary).cuda()
+    d_out = torch.empty_like(d_un)
+    eng.crf_dev(d_un, torch.from_numpy(image).cuda(), api.crf_params(1.0), d_out)
+    assert np.abs(d_out.cpu().numpy() - want).max() <= TOL
+    # SRG with the same label count
+    labels = np.zeros((B, M), np.float32)
+    labels[:, 0] = 1
+    labels[:, M - 1] = 1
+    probs = np.ascontiguousarray(np.transpose(pr, (0, 3, 1, 2)))
+    cues = (rng.rand(B, M, H, W) < 0.02).astype(np.float32)
+    out = torch.empty(B, M, H, W, device="cuda")
+    eng.srg_dev(torch.from_numpy(labels).cuda(), torch.from_numpy(probs).cuda(), torch.from_numpy(cues).cuda(), 0.6, 0.4, out)
+    got = out.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(got[b], srg_oracle.srg_closed_form(labels[b], cues[b], probs[b], 0.6, 0.4))
+    eng.close()
+
+
+def test_label_count_limit_is_reported(torch_cuda):
+    with pytest.raises(api.DsrgError):
+        api.Engine(1, 8, 8, 33)
