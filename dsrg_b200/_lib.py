@@ -51,6 +51,8 @@ SIGNATURES = {
     "dsrg_dsrg_forward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _pp, _d, _d, _vp, _vp, _vp]),
     "dsrg_dsrg_forward_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _pp, _d, _d, _vp, _vp]),
     "dsrg_crflayer_forward_dev": (_i, [_vp, _i, _vp, _vp, _pp, _vp, _vp, _vp]),
+    "dsrg_prepare_image_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dsrg_prepare_image_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "dsrg_wire_pack_mask": (_i, [_vp, _vp, _sz]),
     "dsrg_wire_unpack_mask": (None, [_vp, _vp, _sz]),
     "dsrg_wire_apply_clamp_mask": (None, [_vp, _vp, _sz]),

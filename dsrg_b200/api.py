@@ -162,6 +162,23 @@ class Engine(object):
                                              _hptr(crf_out, np.float32)))
         return seeds_out
 
+    def prepare_image_host(self, images, mean_pixel=(104.0, 117.0, 123.0), out=None):
+        """(B,3,Hi,Wi) float32 network input -> (B,H,W,3) uint8 CRF image (pylayers.py:315-319 + CRF.py:32)."""
+        B, _, Hi, Wi = images.shape
+        if out is None:
+            out = np.empty((B, self.H, self.W, 3), np.uint8)
+        mean = np.asarray(mean_pixel, np.float64)
+        check(self._L.dsrg_prepare_image_host(self.h, B, Hi, Wi, _hptr(images, np.float32), _hptr(mean, np.float64),
+                                              _hptr(out, np.uint8)))
+        return out
+
+    def prepare_image_dev(self, images, out, mean_pixel=(104.0, 117.0, 123.0), stream=None):
+        B, _, Hi, Wi = images.shape
+        mean = np.asarray(mean_pixel, np.float64)
+        check(self._L.dsrg_prepare_image_dev(self.h, B, Hi, Wi, _dptr(images), _hptr(mean, np.float64), _dptr(out),
+                                             _stream(stream)))
+        return out
+
     def crflayer_forward_host(self, probs, image, params, log_out=None, result=None):
         B = probs.shape[0]
         if log_out is None:

@@ -13,12 +13,11 @@ in train-s.prototxt:746-812 keeps working:
   so that the module covers every Python layer train-s.prototxt names except the data layer.
 
 The blobs Caffe hands to a Python layer are host numpy views, so the ``*_host`` entry points of
-the C ABI are used: one H2D of the bottoms and one D2H of the tops per call, everything else on
-the GPU.  There is no multiprocessing.Pool (pylayers.py:292) and no CPU fallback.
+the C ABI are used: one H2D of the bottoms and one D2H of the tops per call, everything else --
+including the image zoom / mean / round preprocessing -- on the GPU.  There is no multiprocessing.Pool (pylayers.py:292) and no CPU fallback.
 """
 import numpy as np
 import yaml
-from scipy.ndimage import zoom
 
 import caffe  # the layers subclass caffe.Layer exactly like the reference (pylayers.py:1)
 
@@ -41,15 +40,11 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def _prepare_image(im, h, w):
-    """pylayers.py:70-75 / :315-319: bilinear zoom to the map size, + mean pixel, np.round; the CRF
-    then casts to ubyte (CRF.py:32)."""
-    mean_pixel = np.array([104.0, 117.0, 123.0])
-    im = zoom(im, (1.0, 1.0, float(h) / im.shape[2], float(w) / im.shape[3]), order=1)
-    im = np.transpose(im, [0, 2, 3, 1])
-    im = im + mean_pixel[None, None, None, :]
-    im = np.round(im)
-    return np.ascontiguousarray(im.astype('ubyte'))
+def _prepare_image(im, eng):
+    """pylayers.py:70-75 / :315-319 (bilinear zoom to the map size, + mean pixel, np.round) and the
+    ubyte cast of CRF.py:32, on the device: dsrg_prepare_image_host is byte-identical to the
+    reference's scipy.ndimage.zoom(order=1) pipeline (tests/test_gpu_dropin.py)."""
+    return eng.prepare_image_host(_f32(im), (104.0, 117.0, 123.0))
 
 
 def _clamped_writeback(blob_data, probs):
@@ -99,8 +94,8 @@ class CRFLayer(caffe.Layer):
     def forward(self, bottom, top):
         n, c, h, w = bottom[0].data.shape
         probs = _f32(bottom[0].data)
-        im = _prepare_image(bottom[1].data[...], h, w)
         eng = _engine(n, c, h, w)
+        im = _prepare_image(bottom[1].data[...], eng)
         log_out = np.empty((n, c, h, w), np.float32)
         self.result = np.empty((n, c, h, w), np.float32)
         eng.crflayer_forward_host(probs, im, _api.crf_params(12.0), log_out, self.result)  # scale_factor=12.0 (:82)
@@ -215,8 +210,8 @@ class DSRGLayer(caffe.Layer):
         """refinement (pylayers.py:310-331) + SRG over the batch (:333-344), fused on the device."""
         num, channels, height, width = probs.shape
         p = _f32(probs)
-        image = _prepare_image(im, height, width)
         eng = _engine(num, channels, height, width)
+        image = _prepare_image(im, eng)
         seeds = eng.dsrg_forward_host(_f32(labels).reshape(num, channels), p, _f32(cues), image,
                                       _api.crf_params(12.0), self._th1, self._th2)
         _clamped_writeback(probs, p)

@@ -146,6 +146,17 @@ int dsrg_dsrg_forward_host(dsrg_engine *e, int B, const float *labels_host, floa
                            const dsrg_crf_params *params, double th1, double th2,
                            float *seeds_out_host, float *crf_out_host);
 
+/*
+ * Image preprocessing of CRFLayer / DSRGLayer (pylayers.py:70-75, :315-319) + the ubyte cast of
+ * CRF.py:32: bilinear zoom (scipy.ndimage.zoom order=1 semantics, float64 arithmetic, bit-exact) of the
+ * [B][3][Hi][Wi] float32 network input to the engine's H x W, + mean_pixel[3], round half to even, ->
+ * [B][H][W][3] uint8, the `image` argument of the entry points above.
+ */
+int dsrg_prepare_image_dev(dsrg_engine *e, int B, int Hi, int Wi, const float *images_dev,
+                           const double *mean_pixel /* host, 3 */, uint8_t *image_out_dev, void *stream);
+int dsrg_prepare_image_host(dsrg_engine *e, int B, int Hi, int Wi, const float *images_host,
+                            const double *mean_pixel /* host, 3 */, uint8_t *image_out_host);
+
 /* Host-only helpers of the *_host wire format (0/1 planes cross PCIe as 1 bit per value, see
  * csrc/wire.cu); exported for unit tests.  pack returns 1 if every value was exactly 0 or 1. */
 int dsrg_wire_pack_mask(const float *src_host, uint32_t *dst_bits, size_t n);

@@ -241,6 +241,28 @@ def prepare_image(im, h, w):
     return np.round(im)
 
 
+def zoom_order1_restated(im, oh, ow):
+    """scipy.ndimage.zoom(im, (1, 1, oh/H, ow/W), order=1) for a (N,C,H,W) float32 array, restated
+    operation by operation (float64 arithmetic, scipy's tap order); tests check it bit-for-bit against
+    scipy and the CUDA kernel against it."""
+    n, c, ih, iw = im.shape
+    zy = (ih - 1) / (oh - 1) if oh > 1 else 0.0
+    zx = (iw - 1) / (ow - 1) if ow > 1 else 0.0
+    ys = np.arange(oh, dtype=np.float64) * zy
+    xs = np.arange(ow, dtype=np.float64) * zx
+    y0 = np.floor(ys).astype(int)
+    x0 = np.floor(xs).astype(int)
+    fy, fx = ys - y0, xs - x0
+    y1, x1 = np.minimum(y0 + 1, ih - 1), np.minimum(x0 + 1, iw - 1)
+    a = im.astype(np.float64)
+    wy0, wx0 = 1 - fy, 1 - fx
+    t = a[:, :, y0][:, :, :, x0] * (wy0[:, None] * wx0[None, :])
+    t = t + a[:, :, y0][:, :, :, x1] * (wy0[:, None] * fx[None, :])
+    t = t + a[:, :, y1][:, :, :, x0] * (fy[:, None] * wx0[None, :])
+    t = t + a[:, :, y1][:, :, :, x1] * (fy[:, None] * fx[None, :])
+    return t.astype(im.dtype)
+
+
 def refinement(probs, im, scale_factor=12.0):
     """DSRGLayer.refinement, pylayers.py:310-331.  Mutates ``probs`` in place like the reference
     (:312).  Returns the float64 N x C x h x w renormalised CRF marginals."""

@@ -56,16 +56,6 @@ def test_dsrg_layer_param_str_and_reshape():
     assert layer2._max_iters == 7
 
 
-def test_image_preparation_follows_reference():
-    from oracle import crf_oracle
-    rng = np.random.RandomState(0)
-    im = (rng.rand(2, 3, 64, 48) * 255 - np.array([104.0, 117.0, 123.0])[None, :, None, None]).astype(np.float32)
-    want = crf_oracle.prepare_image(im, 9, 7)
-    from pylayers import pylayers as impl
-    got = impl._prepare_image(im, 9, 7)
-    assert got.dtype == np.uint8 and np.array_equal(got, want.astype('ubyte'))
-
-
 def _num_grad(f, x, idx, eps=1e-3):
     xp, xm = x.copy(), x.copy()
     xp[idx] += eps

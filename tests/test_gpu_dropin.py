@@ -90,3 +90,20 @@ def test_generate_seed_step_function(torch_cuda):
     seed_c = p["cues"].copy()
     out = pylayers.generate_seed_step([p["labels"], seed_c, p["probs"].astype(np.float64), 0.99, 0.85])
     assert out is seed_c and np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("ih,iw,h,w", [(321, 321, 41, 41), (97, 131, 33, 57), (50, 40, 50, 40), (17, 9, 40, 31)])
+def test_prepare_image_matches_scipy_pipeline(torch_cuda, ih, iw, h, w):
+    """dsrg_prepare_image (zoom order=1 + mean + round + ubyte) == the reference's scipy pipeline, byte for byte."""
+    from dsrg_b200 import api
+    rng = np.random.RandomState(7)
+    im = (rng.rand(3, 3, ih, iw) * 255.0 - np.array([104.0, 117.0, 123.0])[None, :, None, None]).astype(np.float32)
+    im[0, :, :3, :3] = -120.0          # negative after the mean: exercises the ubyte wrap-around
+    want = crf_oracle.prepare_image(im, h, w).astype('ubyte')
+    eng = api.Engine(3, h, w, 21)
+    got = eng.prepare_image_host(im)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    d_out = torch_cuda.empty(3, h, w, 3, dtype=torch_cuda.uint8, device="cuda")
+    eng.prepare_image_dev(torch_cuda.from_numpy(im).cuda(), d_out)
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    eng.close()

@@ -103,3 +103,15 @@ def test_loss_oracle_gradient_is_consistent():
         pm[idx] -= eps
         num = (loss_oracle.balanced_seed_loss(pp, lab) - loss_oracle.balanced_seed_loss(pm, lab)) / (2 * eps)
         assert abs(num - g[idx]) < 1e-5
+
+
+def test_zoom_restatement_is_bit_exact_vs_scipy():
+    """The bilinear-zoom restatement the CUDA preprocessing kernel mirrors, against scipy itself."""
+    from scipy.ndimage import zoom
+    rng = np.random.RandomState(4)
+    for (ih, iw, oh, ow) in ((321, 321, 41, 41), (97, 131, 33, 57), (50, 40, 50, 40), (17, 9, 40, 31), (8, 8, 1, 1),
+                             (5, 7, 1, 4)):
+        im = (rng.rand(2, 3, ih, iw) * 255 - 110).astype(np.float32)
+        want = zoom(im, (1.0, 1.0, float(oh) / ih, float(ow) / iw), order=1)
+        got = crf_oracle.zoom_order1_restated(im, oh, ow)
+        assert want.shape == got.shape and want.dtype == got.dtype and np.array_equal(want, got)
