@@ -51,6 +51,14 @@ SIGNATURES = {
     "dsrg_dsrg_forward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _pp, _d, _d, _vp, _vp, _vp]),
     "dsrg_dsrg_forward_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _pp, _d, _d, _vp, _vp]),
     "dsrg_crflayer_forward_dev": (_i, [_vp, _i, _vp, _vp, _pp, _vp, _vp, _vp]),
+    "dsrg_softmax_forward_dev": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "dsrg_softmax_backward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "dsrg_constrainloss_forward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "dsrg_constrainloss_backward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "dsrg_softmax_forward_host": (_i, [_vp, _i, _vp, _vp]),
+    "dsrg_softmax_backward_host": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "dsrg_constrainloss_forward_host": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "dsrg_constrainloss_backward_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "dsrg_prepare_image_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dsrg_prepare_image_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "dsrg_wire_pack_mask": (_i, [_vp, _vp, _sz]),

@@ -162,6 +162,31 @@ class Engine(object):
                                              _hptr(crf_out, np.float32)))
         return seeds_out
 
+    # ---- SoftmaxLayer / ConstrainLossLayer (host blobs) ----
+    def softmax_forward_host(self, preds):
+        out = np.empty(preds.shape, np.float32)
+        check(self._L.dsrg_softmax_forward_host(self.h, preds.shape[0], _hptr(preds, np.float32), _hptr(out, np.float32)))
+        return out
+
+    def softmax_backward_host(self, preds, top_diff):
+        out = np.empty(preds.shape, np.float32)
+        check(self._L.dsrg_softmax_backward_host(self.h, preds.shape[0], _hptr(preds, np.float32),
+                                                 _hptr(top_diff, np.float32), _hptr(out, np.float32)))
+        return out
+
+    def constrainloss_forward_host(self, probs, log_smooth):
+        out = np.zeros(1, np.float32)
+        check(self._L.dsrg_constrainloss_forward_host(self.h, probs.shape[0], _hptr(probs, np.float32),
+                                                      _hptr(log_smooth, np.float32), _hptr(out, np.float32)))
+        return float(out[0])
+
+    def constrainloss_backward_host(self, probs, log_smooth):
+        gp, gl = np.empty(probs.shape, np.float32), np.empty(probs.shape, np.float32)
+        check(self._L.dsrg_constrainloss_backward_host(self.h, probs.shape[0], _hptr(probs, np.float32),
+                                                       _hptr(log_smooth, np.float32), _hptr(gp, np.float32),
+                                                       _hptr(gl, np.float32)))
+        return gp, gl
+
     def prepare_image_host(self, images, mean_pixel=(104.0, 117.0, 123.0), out=None):
         """(B,3,Hi,Wi) float32 network input -> (B,H,W,3) uint8 CRF image (pylayers.py:315-319 + CRF.py:32)."""
         B, _, Hi, Wi = images.shape

@@ -8,8 +8,8 @@ in train-s.prototxt:746-812 keeps working:
 * ``DSRGLayer``              (pylayers.py:277-344) -> dsrg_dsrg_forward_host
 * ``BalancedSeedLossLayer``  (pylayers.py:120-152) -> dsrg_seedloss_{forward,backward}_host
 * ``generate_seed_step``     (pylayers.py:237-275) -> dsrg_srg_batch_host (batch of one)
-* ``SoftmaxLayer`` / ``ConstrainLossLayer`` (pylayers.py:23-51, :154-180): the producer and the
-  other consumer of the hot path's blobs, restated in numpy on the host for now
+* ``SoftmaxLayer`` / ``ConstrainLossLayer`` (pylayers.py:23-51, :154-180), the producer and the
+  other consumer of the hot path's blobs -> dsrg_softmax_* / dsrg_constrainloss_*,
   so that the module covers every Python layer train-s.prototxt names except the data layer.
 
 The blobs Caffe hands to a Python layer are host numpy views, so the ``*_host`` entry points of
@@ -54,7 +54,7 @@ def _clamped_writeback(blob_data, probs):
 
 
 class SoftmaxLayer(caffe.Layer):
-    """pylayers.py:23-51 (numpy restatement of the Theano graph)."""
+    """pylayers.py:23-51 -> dsrg_softmax_{forward,backward}_host."""
 
     def setup(self, bottom, top):
         if len(bottom) != 1:
@@ -63,22 +63,12 @@ class SoftmaxLayer(caffe.Layer):
     def reshape(self, bottom, top):
         top[0].reshape(*bottom[0].data.shape)
 
-    @staticmethod
-    def _softmax(preds):
-        e = np.exp(preds - np.max(preds, axis=1, keepdims=True))
-        return e / np.sum(e, axis=1, keepdims=True)
-
     def forward(self, bottom, top):
-        s = self._softmax(bottom[0].data[...].astype(np.float32))
-        probs = s + np.float32(min_prob)
-        top[0].data[...] = probs / np.sum(probs, axis=1, keepdims=True)
+        top[0].data[...] = _engine(*bottom[0].data.shape).softmax_forward_host(_f32(bottom[0].data))
 
     def backward(self, top, prop_down, bottom):
-        s = self._softmax(bottom[0].data[...].astype(np.float32))
-        z = np.sum(s + np.float32(min_prob), axis=1, keepdims=True)   # == 1 + C*min_prob
-        # probs = (s + m) / z with z = sum_c (s_c + m): d sum(probs*top_diff) / d s
-        gs = top[0].diff[...] / z - np.sum(top[0].diff[...] * (s + np.float32(min_prob)), axis=1, keepdims=True) / (z * z)
-        bottom[0].diff[...] = s * (gs - np.sum(gs * s, axis=1, keepdims=True))
+        bottom[0].diff[...] = _engine(*bottom[0].data.shape).softmax_backward_host(_f32(bottom[0].data),
+                                                                                  _f32(top[0].diff))
 
 
 class CRFLayer(caffe.Layer):
@@ -139,7 +129,7 @@ def _allreduce_terms(terms, n_local):
 
 
 class ConstrainLossLayer(caffe.Layer):
-    """pylayers.py:154-180 (numpy restatement of the Theano graph)."""
+    """pylayers.py:154-180 -> dsrg_constrainloss_{forward,backward}_host."""
 
     def setup(self, bottom, top):
         if len(bottom) != 2:
@@ -149,18 +139,13 @@ class ConstrainLossLayer(caffe.Layer):
         top[0].reshape(1)
 
     def forward(self, bottom, top):
-        probs = bottom[0].data[...].astype(np.float32)
-        ps = np.exp(bottom[1].data[...].astype(np.float32))
-        top[0].data[...] = np.mean(np.sum(ps * np.log(np.clip(ps / probs, 0.05, 20)), axis=1))
+        top[0].data[...] = _engine(*bottom[0].data.shape).constrainloss_forward_host(_f32(bottom[0].data),
+                                                                                    _f32(bottom[1].data))
 
     def backward(self, top, prop_down, bottom):
-        probs = bottom[0].data[...].astype(np.float32)
-        ps = np.exp(bottom[1].data[...].astype(np.float32))
-        ratio = ps / probs
-        inside = ((ratio >= 0.05) & (ratio <= 20)).astype(np.float32)   # gradient of clip
-        cnt = float(probs.shape[0] * probs.shape[2] * probs.shape[3])   # T.mean over (n, h, w)
-        bottom[0].diff[...] = -(ps / probs) * inside / cnt
-        bottom[1].diff[...] = ps * (np.log(np.clip(ratio, 0.05, 20)) + inside) / cnt
+        gp, gl = _engine(*bottom[0].data.shape).constrainloss_backward_host(_f32(bottom[0].data), _f32(bottom[1].data))
+        bottom[0].diff[...] = gp
+        bottom[1].diff[...] = gl
 
 
 def generate_seed_step(item):

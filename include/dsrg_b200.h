@@ -147,6 +147,27 @@ int dsrg_dsrg_forward_host(dsrg_engine *e, int B, const float *labels_host, floa
                            float *seeds_out_host, float *crf_out_host);
 
 /*
+ * SURVEY 8f rank 1 -- the producer of `probs` and the other consumer of the CRF result:
+ * SoftmaxLayer (pylayers.py:23-51): probs = (softmax(preds) + 1e-4) / sum(...); backward = d sum(probs*top_diff)/d preds.
+ * ConstrainLossLayer (pylayers.py:154-180): loss = mean_{n,h,w} sum_c ps log(clip(ps/probs, 0.05, 20)), ps = exp(log_smooth);
+ * backward writes both gradients (pylayers.py:176-180).  All arrays [B][M][H][W] float32.
+ */
+int dsrg_softmax_forward_dev(dsrg_engine *e, int B, const float *preds_dev, float *probs_out_dev, void *stream);
+int dsrg_softmax_backward_dev(dsrg_engine *e, int B, const float *preds_dev, const float *top_diff_dev,
+                              float *grad_out_dev, void *stream);
+int dsrg_constrainloss_forward_dev(dsrg_engine *e, int B, const float *probs_dev, const float *log_smooth_dev,
+                                   float *loss_out_dev /* 1 float */, void *stream);
+int dsrg_constrainloss_backward_dev(dsrg_engine *e, int B, const float *probs_dev, const float *log_smooth_dev,
+                                    float *grad_probs_dev, float *grad_log_dev, void *stream);
+int dsrg_softmax_forward_host(dsrg_engine *e, int B, const float *preds_host, float *probs_out_host);
+int dsrg_softmax_backward_host(dsrg_engine *e, int B, const float *preds_host, const float *top_diff_host,
+                               float *grad_out_host);
+int dsrg_constrainloss_forward_host(dsrg_engine *e, int B, const float *probs_host, const float *log_smooth_host,
+                                    float *loss_out_host /* 1 float */);
+int dsrg_constrainloss_backward_host(dsrg_engine *e, int B, const float *probs_host, const float *log_smooth_host,
+                                     float *grad_probs_host, float *grad_log_host);
+
+/*
  * Image preprocessing of CRFLayer / DSRGLayer (pylayers.py:70-75, :315-319) + the ubyte cast of
  * CRF.py:32: bilinear zoom (scipy.ndimage.zoom order=1 semantics, float64 arithmetic, bit-exact) of the
  * [B][3][Hi][Wi] float32 network input to the engine's H x W, + mean_pixel[3], round half to even, ->

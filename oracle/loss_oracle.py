@@ -36,3 +36,42 @@ def balanced_seed_loss_grad(probs, labels, dtype=np.float64):
     g[:, 0] = -l[:, 0] / (p[:, 0] * count_bg[:, None, None] * N)
     g[:, 1:] = -l[:, 1:] / (p[:, 1:] * count_fg[:, None, None, None] * N)
     return g
+
+
+# ---- SoftmaxLayer (pylayers.py:23-51) and ConstrainLossLayer (pylayers.py:154-180) ----
+def _softmax(preds):
+    e = np.exp(preds - np.max(preds, axis=1, keepdims=True))
+    return e / np.sum(e, axis=1, keepdims=True)
+
+
+def softmax_layer_forward(preds, dtype=np.float64):
+    """probs = softmax + min_prob, renormalised (pylayers.py:33-36)."""
+    s = _softmax(np.asarray(preds, dtype))
+    probs = s + MIN_PROB
+    return probs / np.sum(probs, axis=1, keepdims=True)
+
+
+def softmax_layer_backward(preds, top_diff, dtype=np.float64):
+    """T.grad(sum(probs * top_diff), preds) (pylayers.py:38-41), analytically."""
+    s = _softmax(np.asarray(preds, dtype))
+    g = np.asarray(top_diff, dtype)
+    z = np.sum(s + MIN_PROB, axis=1, keepdims=True)
+    gs = g / z - np.sum(g * (s + MIN_PROB), axis=1, keepdims=True) / (z * z)
+    return s * (gs - np.sum(gs * s, axis=1, keepdims=True))
+
+
+def constrain_loss(probs, log_smooth, dtype=np.float64):
+    """mean_{n,h,w} sum_c ps * log(clip(ps / probs, 0.05, 20)), ps = exp(log_smooth) (pylayers.py:163-165)."""
+    p = np.asarray(probs, dtype)
+    ps = np.exp(np.asarray(log_smooth, dtype))
+    return float(np.mean(np.sum(ps * np.log(np.clip(ps / p, 0.05, 20)), axis=1)))
+
+
+def constrain_loss_grad(probs, log_smooth, dtype=np.float64):
+    """(d loss / d probs, d loss / d log_smooth) (pylayers.py:168, :176-180)."""
+    p = np.asarray(probs, dtype)
+    ps = np.exp(np.asarray(log_smooth, dtype))
+    ratio = ps / p
+    inside = ((ratio >= 0.05) & (ratio <= 20)).astype(dtype)
+    cnt = float(p.shape[0] * p.shape[2] * p.shape[3])
+    return -(ps / p) * inside / cnt, ps * (np.log(np.clip(ratio, 0.05, 20)) + inside) / cnt

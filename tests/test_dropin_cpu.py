@@ -63,38 +63,21 @@ def _num_grad(f, x, idx, eps=1e-3):
     return (f(xp) - f(xm)) / (2 * eps)
 
 
-def test_softmax_layer_numpy_forward_backward():
+def test_softmax_and_constrain_loss_oracles_are_self_consistent():
+    """The numpy restatements the GPU layers are checked against: analytic backward == numerical gradient."""
+    from oracle import loss_oracle
     rng = np.random.RandomState(1)
-    x = rng.randn(2, 5, 3, 4).astype(np.float32)
-    layer, bottom, top = fake_caffe.run_layer(pylayers.SoftmaxLayer, [x])
-    p = top[0].data
-    np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-6)
-    e = np.exp(x - x.max(1, keepdims=True))
-    ref = e / e.sum(1, keepdims=True) + 1e-4
-    np.testing.assert_allclose(p, ref / ref.sum(1, keepdims=True), rtol=1e-5)
-    g = rng.randn(*x.shape).astype(np.float32)
-    top[0].diff[...] = g
-    layer.backward(top, [True], bottom)
-
-    def f(xx):
-        ee = np.exp(xx - xx.max(1, keepdims=True))
-        pp = ee / ee.sum(1, keepdims=True) + 1e-4
-        return float(np.sum(pp / pp.sum(1, keepdims=True) * g))
+    x = rng.randn(2, 5, 3, 4)
+    g = rng.randn(*x.shape)
+    p = loss_oracle.softmax_layer_forward(x)
+    np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-12)
+    gx = loss_oracle.softmax_layer_backward(x, g)
     for idx in [(0, 1, 2, 3), (1, 4, 0, 0)]:
-        assert abs(_num_grad(f, x.astype(np.float64), idx, 1e-4) - bottom[0].diff[idx]) < 2e-3
-
-
-def test_constrain_loss_layer_numpy_forward_backward():
-    rng = np.random.RandomState(2)
-    p = rng.rand(2, 4, 3, 3).astype(np.float32) * 0.8 + 0.1
-    ls = np.log(rng.rand(2, 4, 3, 3).astype(np.float32) * 0.8 + 0.1)
-    layer, bottom, top = fake_caffe.run_layer(pylayers.ConstrainLossLayer, [p, ls])
-
-    def f(pp, ll):
-        ps = np.exp(ll)
-        return float(np.mean(np.sum(ps * np.log(np.clip(ps / pp, 0.05, 20)), axis=1)))
-    assert abs(float(top[0].data[0]) - f(p.astype(np.float64), ls.astype(np.float64))) < 1e-5
-    layer.backward(top, [True, True], bottom)
-    for idx in [(0, 1, 2, 2), (1, 3, 0, 1)]:
-        assert abs(_num_grad(lambda q: f(q, ls.astype(np.float64)), p.astype(np.float64), idx, 1e-5) - bottom[0].diff[idx]) < 1e-3
-        assert abs(_num_grad(lambda q: f(p.astype(np.float64), q), ls.astype(np.float64), idx, 1e-5) - bottom[1].diff[idx]) < 1e-3
+        assert abs(_num_grad(lambda q: float(np.sum(loss_oracle.softmax_layer_forward(q) * g)), x, idx, 1e-5) - gx[idx]) < 1e-7
+    pr = rng.rand(2, 4, 3, 3) * 0.8 + 0.1
+    ls = np.log(rng.rand(2, 4, 3, 3) * 0.8 + 0.1)
+    ls[0, 0, 0, 0] = np.log(1e-3)          # ratio below 0.05: clipped branch
+    gp, gl = loss_oracle.constrain_loss_grad(pr, ls)
+    for idx in [(0, 1, 2, 2), (1, 3, 0, 1), (0, 0, 0, 0)]:
+        assert abs(_num_grad(lambda q: loss_oracle.constrain_loss(q, ls), pr, idx, 1e-6) - gp[idx]) < 1e-6
+        assert abs(_num_grad(lambda q: loss_oracle.constrain_loss(pr, q), ls, idx, 1e-6) - gl[idx]) < 1e-6

@@ -107,3 +107,27 @@ def test_prepare_image_matches_scipy_pipeline(torch_cuda, ih, iw, h, w):
     eng.prepare_image_dev(torch_cuda.from_numpy(im).cuda(), d_out)
     assert np.array_equal(d_out.cpu().numpy(), want)
     eng.close()
+
+
+def test_softmax_and_constrain_loss_layers(torch_cuda):
+    """SoftmaxLayer / ConstrainLossLayer on the device vs the float64 numpy restatements (float32 kernels, rtol 2e-5)."""
+    rng = np.random.RandomState(3)
+    x = (rng.randn(3, 21, 41, 41) * 3).astype(np.float32)
+    layer, bottom, top = fake_caffe.run_layer(pylayers.SoftmaxLayer, [x])
+    np.testing.assert_allclose(top[0].data, loss_oracle.softmax_layer_forward(x), rtol=2e-5, atol=1e-9)
+    g = rng.randn(*x.shape).astype(np.float32)
+    top[0].diff[...] = g
+    layer.backward(top, [True], bottom)
+    np.testing.assert_allclose(bottom[0].diff, loss_oracle.softmax_layer_backward(x, g), rtol=2e-4, atol=2e-7)
+    probs = top[0].data.copy()
+    logs = np.log(loss_oracle.softmax_layer_forward((rng.randn(*x.shape) * 3).astype(np.float32))).astype(np.float32)
+    layer, bottom, top = fake_caffe.run_layer(pylayers.ConstrainLossLayer, [probs, logs])
+    want = loss_oracle.constrain_loss(probs, logs)
+    assert abs(float(top[0].data[0]) - want) <= 2e-5 * abs(want)
+    layer.backward(top, [True, True], bottom)
+    gp, gl = loss_oracle.constrain_loss_grad(probs.astype(np.float64), logs.astype(np.float64))
+    # elements sitting exactly on a clip boundary in float32 vs float64 may take the other branch
+    ratio = np.exp(logs.astype(np.float64)) / probs
+    safe = (np.abs(ratio - 0.05) > 1e-5) & (np.abs(ratio - 20) > 1e-3)
+    np.testing.assert_allclose(bottom[0].diff[safe], gp[safe], rtol=2e-4, atol=1e-9)
+    np.testing.assert_allclose(bottom[1].diff[safe], gl[safe], rtol=2e-4, atol=1e-9)
