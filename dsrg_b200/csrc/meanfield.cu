@@ -396,7 +396,8 @@ k_mf_zero(float4 *a, const int32_t *rowbase_a, float4 *c, const int32_t *rowbase
 // ---------------------------------------------------------------------------------------------
 template <int MP>
 __global__ void __launch_bounds__(kThreads)
-k_mf_blur(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase, int b0, int nb, int shared) {
+k_mf_blur(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase, int b0, int nb, int shared,
+          float4 *zero) {
     constexpr int CH = MP / 4;
     const long long r0 = rowbase[b0], rows = rowbase[b0 + nb] - r0;
     const int rows_img = shared ? rowbase[1] : 0;
@@ -424,6 +425,9 @@ k_mf_blur(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase
         r.z = o.z + 0.5f * (a.z + d.z);
         r.w = o.w + 0.5f * (a.w + d.w);
         out[g * CH + c] = r;
+        // the buffer that was sliced in this iteration is dead by now: clear it here so that it can be
+        // the next splat target without a separate zeroing pass
+        if (zero) zero[g * CH + c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -503,14 +507,14 @@ static TileLat make_tile_view(const Lattice &L, const float *val_in, float *val_
 // blur `buf` (just splatted) along all d+1 axes for images [b0, b0+nb), ping-ponging with `tmp`;
 // returns where the result lives
 template <int MP>
-static float *blur_all(Engine *e, const Lattice &L, float *buf, float *tmp, int b0, int nb, int tag, int grid,
-                       cudaStream_t s) {
+static float *blur_all(Engine *e, const Lattice &L, float *buf, float *tmp, float *dead, int b0, int nb, int tag,
+                       int grid, cudaStream_t s) {
     float *src = buf, *dst = tmp;
     for (int j = 0; j <= L.d; j++) {
         DSRG_LAUNCH(e, tag, s,
                     k_mf_blur<MP><<<grid, kThreads, 0, s>>>((const float4 *)src, (float4 *)dst,
                                                             L.nbr + (size_t)j * L.nbr_stride, L.rowbase, b0, nb,
-                                                            L.shared));
+                                                            L.shared, j == 0 ? (float4 *)dead : nullptr));
         float *t = src;
         src = dst;
         dst = t;
@@ -588,12 +592,9 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
                                                                              N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));
                 continue;
             }
-            // the old X is dead: it becomes the next (zeroed) splat target
-            DSRG_LAUNCH(e, T_MF_ZERO, st,
-                        k_mf_zero<MP><<<bgrid, kThreads, 0, st>>>((float4 *)spX, e->sp.rowbase, (float4 *)biX,
-                                                                    e->bi.rowbase, b0, nb));
-            sp_res = blur_all<MP>(e, e->sp, spY, spZ, b0, nb, T_MF_BLUR_SP, bgrid, st);
-            bi_res = blur_all<MP>(e, e->bi, biY, biZ, b0, nb, T_MF_BLUR_BI, bgrid, st);
+            // the old X is dead: the first blur pass clears it and it becomes the next splat target
+            sp_res = blur_all<MP>(e, e->sp, spY, spZ, spX, b0, nb, T_MF_BLUR_SP, bgrid, st);
+            bi_res = blur_all<MP>(e, e->bi, biY, biZ, biX, b0, nb, T_MF_BLUR_BI, bgrid, st);
         }
         if (it == T) break;
         float *sp_other = (sp_res == spY) ? spZ : spY, *bi_other = (bi_res == biY) ? biZ : biY;
