@@ -33,10 +33,21 @@ def needs_build():
 
 
 def build(force=False, verbose=False, defines=(), out=None):
-    """defines/out: build an experimental variant (extra -D flags) next to the main library."""
-    if out is None and not force and not needs_build():
-        return LIB
+    """defines/out: build an experimental variant (extra -D flags) next to the main library.
+    Serialised with a file lock: under torchrun every rank may find the library stale at once."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose, defines, out)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose, defines, out):
+    if out is None and not force and not needs_build():   # re-checked under the lock
+        return LIB
     lib = out or LIB
     objdir = os.path.join(LIBDIR, "obj" if out is None else "obj_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
