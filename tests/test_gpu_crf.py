@@ -151,3 +151,61 @@ def test_crf_and_srg_other_label_counts(torch_cuda, M):
 def test_label_count_limit_is_reported(torch_cuda):
     with pytest.raises(api.DsrgError):
         api.Engine(1, 8, 8, 33)
+
+
+@pytest.mark.parametrize("n_iters", [0, 1, 2, 3])
+def test_crf_iteration_counts(torch_cuda, n_iters):
+    """maxiter = 0 returns softmax(unary) (densecrf.cpp:120); 1 and 2 exercise the first / last / middle
+    variants of the fused kernel."""
+    torch = torch_cuda
+    B, H, W, M = 2, 33, 47, 21
+    batch = synth.make_batch(B, H, W, image="smooth", start=21)
+    unary = np.ascontiguousarray(np.log(np.maximum(np.transpose(batch["probs"], (0, 2, 3, 1)), 1e-5)), np.float32)
+    want = np.stack([crf_oracle.CRF(batch["image"][b], unary[b], n_iters, 1.0) for b in range(B)])
+    eng = api.Engine(B, H, W, M)
+    for layout in (api.LAYOUT_NHWC, api.LAYOUT_NCHW):
+        u = unary if layout == api.LAYOUT_NHWC else np.ascontiguousarray(np.transpose(unary, (0, 3, 1, 2)))
+        d_un = torch.from_numpy(u).cuda()
+        d_out = torch.empty_like(d_un)
+        eng.crf_dev(d_un, torch.from_numpy(batch["image"]).cuda(), api.crf_params(1.0, maxiter=n_iters), d_out, layout, layout)
+        got = d_out.cpu().numpy()
+        if layout == api.LAYOUT_NCHW:
+            got = np.transpose(got, (0, 2, 3, 1))
+        assert np.abs(got - want).max() <= TOL
+    eng.close()
+
+
+def test_engine_reuse_changing_parameters_and_batch(torch_cuda):
+    """One engine, many calls: partial batches, changing sigmas (the spatial lattice cache must be
+    invalidated), changing images; every call must still match a fresh oracle run."""
+    torch = torch_cuda
+    H, W, M, Bmax = 40, 52, 21, 5
+    eng = api.Engine(Bmax, H, W, M)
+    calls = [(5, 1.0, 13, "smooth", 0), (2, 12.0, 13, "noise", 9), (3, 1.0, 13, "smooth", 4), (1, 3.0, 20, "smooth", 2),
+             (5, 1.0, 13, "smooth", 0)]
+    for B, sf, cf, img, start in calls:
+        batch = synth.make_batch(B, H, W, image=img, start=start)
+        unary = np.ascontiguousarray(np.transpose(batch["probs"], (0, 2, 3, 1)))
+        want = np.stack([crf_oracle.CRF(batch["image"][b], unary[b], 10, sf, cf) for b in range(B)])
+        got = eng.crf_host(unary, batch["image"], api.crf_params(sf, cf, 10))
+        assert np.abs(got - want).max() <= TOL, (B, sf, cf, img)
+    eng.close()
+
+
+def test_crf_random_shapes_fuzz(torch_cuda):
+    """Seeded fuzz over small odd shapes (narrower than a tile, single rows / columns, ...)."""
+    rng = np.random.RandomState(2024)
+    for case in range(10):
+        H, W = int(rng.randint(1, 70)), int(rng.randint(1, 70))
+        M = int(rng.choice([3, 21]))
+        sf = float(rng.choice([1.0, 12.0]))
+        B = int(rng.randint(1, 4))
+        logits = rng.randn(B, H, W, M).astype(np.float32)
+        unary = logits - np.log(np.exp(logits).sum(-1, keepdims=True))
+        image = rng.randint(0, 256, (B, H, W, 3)).astype(np.uint8) if case % 2 else \
+            np.stack([synth.make_image(rng, H, W, "smooth") for _ in range(B)])
+        want = np.stack([crf_oracle.CRF(image[b], unary[b], 10, sf) for b in range(B)])
+        eng = api.Engine(B, H, W, M)
+        got = eng.crf_host(np.ascontiguousarray(unary, np.float32), np.ascontiguousarray(image), api.crf_params(sf))
+        assert np.abs(got - want).max() <= TOL, (case, H, W, M, sf, B)
+        eng.close()

@@ -139,3 +139,55 @@ def test_dsrg_forward_host_pipelined_chunks(torch_cuda):
     assert np.abs(outs[0][1] - outs[1][1]).max() <= 2e-5
     assert (outs[0][0] != outs[1][0]).mean() <= 1e-4
     eng.close()
+
+
+def _pattern_problem(mask, C=21, fg=5):
+    """probs/cues such that class `fg` passes the threshold exactly on `mask`; one seed on the first mask pixel."""
+    H, W = mask.shape
+    probs = np.full((C, H, W), 0.001, np.float32)
+    probs[0] = 0.5                       # background never reaches th1 = 0.99
+    probs[fg][mask] = 0.9
+    probs[0][mask] = 0.05
+    labels = np.zeros(C, np.float32)
+    labels[0] = labels[fg] = 1
+    cues = np.zeros((C, H, W), np.float32)
+    ys, xs = np.nonzero(mask)
+    cues[fg, ys[0], xs[0]] = 1
+    return labels, probs, cues
+
+
+def test_srg_adversarial_connectivity(torch_cuda):
+    """Long 1-pixel chains (spiral, serpentine), a diagonal-only checkerboard and a comb: worst cases for the
+    lock-free union-find and the warp-ballot run linking.  One seed must flood exactly its component."""
+    H, W = 97, 131
+    masks = {}
+    ser = np.zeros((H, W), bool)
+    for y in range(0, H, 2):
+        ser[y, :] = True
+        if y + 1 < H:
+            ser[y + 1, (W - 1) if (y // 2) % 2 == 0 else 0] = True
+    masks["serpentine"] = ser
+    sp = np.zeros((H, W), bool)
+    t, b, l, r = 0, H - 1, 0, W - 1
+    while t <= b and l <= r:
+        sp[t, l:r + 1] = True
+        sp[t:b + 1, r] = True
+        if b - t >= 2 and r - l >= 2:
+            sp[b, l + 2:r + 1] = True
+            sp[t + 2:b + 1, l + 2] = True
+        t, b, l, r = t + 4, b - 4, l + 4, r - 4
+    masks["spiral-ish"] = sp
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks["checkerboard"] = (yy + xx) % 2 == 0          # connected only through diagonals
+    comb = np.zeros((H, W), bool)
+    comb[0, :] = True
+    comb[:, ::2] = True
+    masks["comb"] = comb
+    labels, probs, cues = zip(*[_pattern_problem(m) for m in masks.values()])
+    labels, probs, cues = np.stack(labels), np.stack(probs), np.stack(cues)
+    got = run_gpu_srg(torch_cuda, labels, cues, probs)
+    for i, (name, m) in enumerate(masks.items()):
+        want = srg_oracle.srg_closed_form(labels[i], cues[i], probs[i], 0.99, 0.85)
+        assert np.array_equal(got[i], want), name
+        grown = got[i, 5] > 0
+        assert not (grown & ~m).any(), name
