@@ -41,16 +41,38 @@ k_float_to_bits(const float *in, uint32_t *bits, int n_img, int wpi) {
 
 // ---- host side: ONE OpenMP region per chunk and operation (images x word blocks), SSE2 inside --
 // (many small regions with many threads were measured to be slower than the PCIe time they save)
+// CPUs this process may really use: the cgroup quota (the GPU boxes give a 128-thread host a 16-CPU
+// quota; oversubscribing it was measured 2x slower), shared among the ranks of a torchrun launch.
+static int cpu_budget() {
+    int n = omp_get_max_threads();
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        long long quota = 0, period = 0;
+        char q[32] = {0};
+        if (fscanf(f, "%31s %lld", q, &period) == 2 && q[0] != 'm' && period > 0) {
+            quota = atoll(q);
+            const int c = (int)((quota + period - 1) / period);
+            if (c >= 1 && c < n) n = c;
+        }
+        fclose(f);
+    }
+    int ranks = 1;
+    if (const char *ev = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(ev) > 0 ? atoi(ev) : 1;
+    n /= ranks;
+    return n < 1 ? 1 : n;
+}
+
 static int host_threads() {
     static int n = 0;
     if (!n) {
-        n = omp_get_max_threads() / 2;
+        n = cpu_budget();
         if (n > 16) n = 16;
         if (const char *ev = getenv("DSRG_B200_HOST_THREADS")) n = atoi(ev);
         if (n < 1) n = 1;
     }
     return n;
 }
+// packing 0/1 planes on the host only pays when enough cores are available to outrun PCIe
+static bool wire_worthwhile() { return host_threads() >= 6; }
 constexpr int kWireBlocks = 16;  // word blocks per image
 
 static inline void block_range(size_t total, int blk, size_t &lo, size_t &hi) {
@@ -250,7 +272,7 @@ static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, c
         t_issue += omp_get_wtime() - ti;
         // ---- host: pack this chunk's cues (1 bit per value) unless they are not a 0/1 mask
         const double tp = omp_get_wtime();
-        const bool ok = e->wire_compress != 0 &&
+        const bool ok = e->wire_compress != 0 && wire_worthwhile() &&
                         pack_mask(cues + (size_t)b0 * img_elems, e->h_cbits + (size_t)b0 * wpi, img_elems, wpi, nb);
         t_pack += omp_get_wtime() - tp;
         ti = omp_get_wtime();
