@@ -143,7 +143,7 @@ struct Engine {
     cudaEvent_t fork_event = nullptr, join_event = nullptr;
     int lanes = 1;  // 2 = run the mean-field loop as two half-batches on two streams (measured: +1 %, off)
     std::vector<cudaEvent_t> pipe_events;
-    int host_chunk = 16;  // images per (full) pipeline stage of the *_host entry points
+    int host_chunk = 0;   // > 0 caps the images per pipeline stage of the *_host entry points
     // 0/1 planes travel over PCIe as bit masks (wire.cu): device + pinned host staging, [maxB][words/image]
     uint32_t *d_cbits = nullptr, *d_sbits = nullptr, *d_mbits = nullptr;
     uint32_t *h_cbits = nullptr, *h_sbits = nullptr, *h_mbits = nullptr;

@@ -230,14 +230,42 @@ static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, c
     if ((rc = ensure_staging(e))) return rc;
     if ((rc = ensure_wire(e))) return rc;
     // chunk schedule: a small first chunk gets the GPU going early, then full-size chunks
-    const int chunk = e->host_chunk > 0 ? e->host_chunk : 16;
+    const int chunk = e->host_chunk > 0 ? e->host_chunk : B;
     std::vector<int> cb0, cnb;
-    for (int b = 0, step = chunk >= 8 ? chunk / 4 : chunk; b < B;) {
-        const int nb = (B - b < step) ? B - b : step;
-        cb0.push_back(b);
-        cnb.push_back(nb);
-        b += nb;
-        step = (step * 2 < chunk) ? step * 2 : chunk;
+    if (const char *ev = getenv("DSRG_B200_HOST_SCHEDULE")) {  // e.g. "4,12,16,32": explicit chunk sizes (tuning aid)
+        int b = 0;
+        for (const char *p = ev; *p && b < B;) {
+            int v = atoi(p);
+            if (v < 1) break;
+            if (v > e->maxB) v = e->maxB;
+            if (v > B - b) v = B - b;
+            cb0.push_back(b);
+            cnb.push_back(v);
+            b += v;
+            while (*p && *p != ',') p++;
+            if (*p == ',') p++;
+        }
+        while (b < B) {
+            const int v = (B - b < chunk) ? B - b : chunk;
+            cb0.push_back(b);
+            cnb.push_back(v);
+            b += v;
+        }
+    }
+    if (cb0.empty()) {
+        // default: B/8, 3B/8, B/2 (8 | 24 | 32 of 64: measured best of the schedules tried -- a short first
+        // chunk gets the GPU going, big later chunks keep its kernels efficient); a positive host_chunk
+        // caps the chunk size instead
+        const int cap = e->host_chunk > 0 ? e->host_chunk : B;
+        const int want[3] = {(B + 7) / 8, (3 * B + 7) / 8, B};
+        for (int b = 0, k = 0; b < B; k++) {
+            int nb = want[k < 2 ? k : 2];
+            if (nb > cap) nb = cap;
+            if (nb > B - b) nb = B - b;
+            cb0.push_back(b);
+            cnb.push_back(nb);
+            b += nb;
+        }
     }
     const int nchunks = (int)cb0.size();
     while ((int)e->pipe_events.size() < 3 * nchunks) {

@@ -74,8 +74,8 @@ typedef struct dsrg_engine dsrg_engine;
 dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M);
 void dsrg_engine_destroy(dsrg_engine *e);
 size_t dsrg_engine_device_bytes(const dsrg_engine *e); /* bytes of HBM held by the engine */
-/* The *_host full-pass entry point pipelines the batch in chunks of `images` (default 16, after a short ramp-up) through
- * H2D | kernels | D2H streams; 0 restores the default. */
+/* The *_host full-pass entry points pipeline the batch in chunks (default B/8, 3B/8, B/2 images) through
+ * H2D | kernels | D2H streams; `images` > 0 caps the chunk size, 0 restores the default. */
 int dsrg_engine_set_host_chunk(dsrg_engine *e, int images);
 /* Experimental: run the mean-field loop as `lanes` (1 or 2, default 1) half-batches on separate
  * streams so that the DRAM-latency-bound blur passes of one half overlap the shared-memory-bound tile
