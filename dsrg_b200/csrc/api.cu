@@ -284,7 +284,6 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     const size_t n = (size_t)max_batch * M * e->N;
     rc |= dalloc(e, &e->U, n);
     rc |= dalloc(e, &e->Q0, n);
-    rc |= dalloc(e, &e->Q1, n);
     rc |= dalloc(e, &e->spA, (size_t)e->sp.rows_cap * e->MP);
     rc |= dalloc(e, &e->spB, (size_t)e->sp.rows_cap * e->MP);
     rc |= dalloc(e, &e->spC, (size_t)e->sp.rows_cap * e->MP);
@@ -325,7 +324,7 @@ void dsrg_engine_destroy(dsrg_engine *h) {
     cudaDeviceSynchronize();
     lattice_free(e->sp);
     lattice_free(e->bi);
-    void *ptrs[] = {e->U, e->Q0, e->Q1, e->spA, e->spB, e->spC, e->biA, e->biB, e->biC, e->nvA, e->nvB, e->lmap,
+    void *ptrs[] = {e->U, e->Q0, e->spA, e->spB, e->spC, e->biA, e->biB, e->biC, e->nvA, e->nvB, e->lmap,
                     e->lflag, e->parent, e->hc, e->loss_acc, e->dev_err, e->st_unary, e->st_out,
                     e->st_cues, e->st_labels, e->st_image, e->st_lmap, e->st_raw};
     for (void *p : ptrs) cudaFree(p);

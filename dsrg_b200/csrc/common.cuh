@@ -118,8 +118,8 @@ struct Engine {
     bool sp_valid = false;
 
     // mean-field state, planar [B][M][N]
-    float *U = nullptr, *Q0 = nullptr, *Q1 = nullptr;
-    float *Qcur = nullptr;  // where the current marginals live (Q0 or Q1)
+    float *U = nullptr, *Q0 = nullptr;
+    float *Qcur = nullptr;  // where the current marginals live
     // lattice value buffers [rows][MP]
     float *spA = nullptr, *spB = nullptr, *spC = nullptr, *biA = nullptr, *biB = nullptr, *biC = nullptr;
     int tiles_x = 0, tiles_y = 0, ntiles = 0;  // tiles of tile_w x 8 pixels
