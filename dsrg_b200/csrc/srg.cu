@@ -45,10 +45,15 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
 }
 
 // K1 --------------------------------------------------------------------------------------------
+// MT > 0: the label count is a compile-time constant, so all 2*MT loads of a pixel are issued before the
+// first use (the kernel is a stream of 2*MT planes and was latency-bound at 41 % of DRAM peak);
+// MT == 0: generic run-time loop.
+template <int MT>
 __global__ void __launch_bounds__(kThreads)
-k_srg_label(const float *labels, const float *probs, const float *cues, double th1, double th2,
-            int renorm, uint8_t *lmap, uint8_t *lflag, int32_t *parent, uint8_t *hc,
-            int32_t *label_map_out, int M, int N, int W) {
+k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, const float *__restrict__ cues,
+            double th1, double th2, int renorm, uint8_t *lmap, uint8_t *lflag, int32_t *parent, uint8_t *hc,
+            int32_t *label_map_out, int Mrt, int N, int W) {
+    const int M = MT ? MT : Mrt;
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < N;
@@ -67,15 +72,23 @@ k_srg_label(const float *labels, const float *probs, const float *cues, double t
         double best = 0.0, s = 0.0;
         float nseed = 0.0f;   // np.sum(seed_c[:, x, y]) (pylayers.py:268)
         float cue_at_L = 0.0f;
-#pragma unroll 7
+        float cuv[MT ? MT : 1], pv[MT ? MT : 1];
+        if (MT) {
+#pragma unroll
+            for (int c = 0; c < (MT ? MT : 1); c++) {
+                cuv[c] = __ldg(cb + (size_t)c * N);
+                pv[c] = __ldg(pb + (size_t)c * N);
+            }
+        }
+#pragma unroll
         for (int c = 0; c < M; c++) {
-            const float cu = cb[(size_t)c * N];
+            const float cu = MT ? cuv[MT ? c : 0] : cb[(size_t)c * N];
             nseed += cu;
             if (cu > 0.0f) {  // seeds: the highest class index wins (pylayers.py:248-250)
                 L = c + 1;
                 cue_at_L = cu;
             }
-            double v = (double)pb[(size_t)c * N];
+            double v = (double)(MT ? pv[MT ? c : 0] : pb[(size_t)c * N]);
             if (renorm) {
                 if (v < 0.0001) v = 0.0001;
                 s += v;  // sequential float64 sum over classes, like np.sum(axis=1)
@@ -154,9 +167,11 @@ k_srg_flag(const uint8_t *lflag, int32_t *parent, uint8_t *hc, int N) {
 }
 
 // K4 --------------------------------------------------------------------------------------------
+template <int MT>
 __global__ void __launch_bounds__(kThreads)
-k_srg_emit(const float *cues, const uint8_t *lmap, const uint8_t *lflag, const int32_t *parent,
-           const uint8_t *hc, float *seeds_out, int M, int N) {
+k_srg_emit(const float *__restrict__ cues, const uint8_t *lmap, const uint8_t *lflag, const int32_t *parent,
+           const uint8_t *hc, float *__restrict__ seeds_out, int Mrt, int N) {
+    const int M = MT ? MT : Mrt;
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -169,8 +184,15 @@ k_srg_emit(const float *cues, const uint8_t *lmap, const uint8_t *lflag, const i
     }
     const float *cb = cues + (size_t)b * M * N + i;
     float *ob = seeds_out + (size_t)b * M * N + i;
-#pragma unroll 7
-    for (int c = 0; c < M; c++) ob[(size_t)c * N] = (c == grow_c) ? 1.0f : cb[(size_t)c * N];
+    if (MT) {
+        float v[MT ? MT : 1];
+#pragma unroll
+        for (int c = 0; c < (MT ? MT : 1); c++) v[c] = __ldg(cb + (size_t)c * N);
+#pragma unroll
+        for (int c = 0; c < (MT ? MT : 1); c++) ob[(size_t)c * N] = (c == grow_c) ? 1.0f : v[c];
+    } else {
+        for (int c = 0; c < M; c++) ob[(size_t)c * N] = (c == grow_c) ? 1.0f : cb[(size_t)c * N];
+    }
 }
 
 int srg_run(Engine *e, int B, const float *labels, const float *probs, const float *cues,
@@ -178,13 +200,22 @@ int srg_run(Engine *e, int B, const float *labels, const float *probs, const flo
             cudaStream_t s) {
     const int N = e->N, M = e->M;
     dim3 g(cdiv(N, kThreads), B);
-    DSRG_LAUNCH(e, T_SRG_LABEL, s,
-                k_srg_label<<<g, kThreads, 0, s>>>(labels, probs, cues, th1, th2, renorm, e->lmap, e->lflag,
-                                                   e->parent, e->hc, label_map_out, M, N, e->W));
+    if (M == 21)
+        DSRG_LAUNCH(e, T_SRG_LABEL, s,
+                    k_srg_label<21><<<g, kThreads, 0, s>>>(labels, probs, cues, th1, th2, renorm, e->lmap, e->lflag,
+                                                           e->parent, e->hc, label_map_out, M, N, e->W));
+    else
+        DSRG_LAUNCH(e, T_SRG_LABEL, s,
+                    k_srg_label<0><<<g, kThreads, 0, s>>>(labels, probs, cues, th1, th2, renorm, e->lmap, e->lflag,
+                                                          e->parent, e->hc, label_map_out, M, N, e->W));
     DSRG_LAUNCH(e, T_SRG_MERGE, s, k_srg_merge<<<g, kThreads, 0, s>>>(e->lmap, e->parent, N, e->W));
     DSRG_LAUNCH(e, T_SRG_FLAG, s, k_srg_flag<<<g, kThreads, 0, s>>>(e->lflag, e->parent, e->hc, N));
-    DSRG_LAUNCH(e, T_SRG_EMIT, s,
-                k_srg_emit<<<g, kThreads, 0, s>>>(cues, e->lmap, e->lflag, e->parent, e->hc, seeds_out, M, N));
+    if (M == 21)
+        DSRG_LAUNCH(e, T_SRG_EMIT, s,
+                    k_srg_emit<21><<<g, kThreads, 0, s>>>(cues, e->lmap, e->lflag, e->parent, e->hc, seeds_out, M, N));
+    else
+        DSRG_LAUNCH(e, T_SRG_EMIT, s,
+                    k_srg_emit<0><<<g, kThreads, 0, s>>>(cues, e->lmap, e->lflag, e->parent, e->hc, seeds_out, M, N));
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }
