@@ -13,6 +13,7 @@
 // calling thread packs the next chunk and unpacks finished ones.
 #include <emmintrin.h>
 #include <omp.h>
+#include <unistd.h>
 
 #include "common.cuh"
 
@@ -44,7 +45,9 @@ k_float_to_bits(const float *in, uint32_t *bits, int n_img, int wpi) {
 // CPUs this process may really use: the cgroup quota (the GPU boxes give a 128-thread host a 16-CPU
 // quota; oversubscribing it was measured 2x slower), shared among the ranks of a torchrun launch.
 static int cpu_budget() {
-    int n = omp_get_max_threads();
+    // (not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1; the num_threads clauses below override it)
+    long onl = sysconf(_SC_NPROCESSORS_ONLN);
+    int n = onl > 0 ? (int)onl : 1;
     if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
         long long quota = 0, period = 0;
         char q[32] = {0};
