@@ -562,7 +562,10 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
         DSRG_CUDA_TRY(cudaEventRecord(e->fork_event, s));
         DSRG_CUDA_TRY(cudaStreamWaitEvent(e->aux_stream, e->fork_event, 0));
     }
-    const int bgrid = (8 * e->sm_count) / nlanes;
+#ifndef DSRG_BLUR_GRID
+#define DSRG_BLUR_GRID 8
+#endif
+    const int bgrid = (DSRG_BLUR_GRID * e->sm_count) / nlanes;
     // three value buffers per lattice: X = blurred values being sliced, Y = zeroed splat target,
     // Z = blur scratch (the lanes use disjoint row ranges of the same buffers)
     float *spX = e->spA, *spY = e->spB, *spZ = e->spC;
