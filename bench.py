@@ -133,6 +133,22 @@ class ClockSampler(object):
 IMAGE_VARIANT = "smooth"
 
 
+def usable_cpus():
+    """CPUs this process can really use: affinity mask, further limited by the cgroup CPU quota (the GPU
+    boxes expose 128 logical CPUs with a 16-CPU quota; oversubscribing only adds context switches)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def synth_batch(H, W, B, unique=8):
     from dsrg_b200 import synth
     return synth.make_batch(B, H, W, cues="cam", image=IMAGE_VARIANT, unique=unique)
@@ -182,10 +198,7 @@ def run_reference(args, rank, world):
     from oracle import crf_oracle
     crf_oracle.build()
     H, W, B, what = WORKLOADS[args.workload]
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        cores = os.cpu_count() or 1
+    cores = usable_cpus()
     cores = max(1, min(cores, 64))  # every host thread we may use, capped at the batch size (26 MB pickled per image)
     n = cores  # one image per core per step: a bounded sample of the batch-64 workload
     batch = synth_batch(H, W, min(n, 8), unique=8)
