@@ -372,7 +372,9 @@ def run_b200(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * B * args.steps / dt, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "api": "dsrg_*_host (C ABI, pinned host buffers)"}
+               "d2h_bytes_per_step": int(d2h), "api": "dsrg_*_host (C ABI, pinned host buffers)",
+               "note": "inputs are re-sent from the same pinned buffers every step; the in-place 1e-4 clamp of probs "
+                       "(pylayers.py:312) therefore only changes values during the first warm-up step"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
