@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("DSRG_B200_LIB") or os.path.join(_HERE, "lib", "libdsr
 
 OK, E_INVALID, E_CUDA, E_KEYRANGE, E_STATE, E_NOMEM = 0, -1, -2, -3, -4, -5
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
+POST_SUM_SCORES, POST_ZOOM_PROBS = 0, 1
 
 
 class DsrgError(RuntimeError):
@@ -40,6 +41,8 @@ SIGNATURES = {
     "dsrg_engine_create": (_vp, [_i, _i, _i, _i, _i]),
     "dsrg_engine_destroy": (None, [_vp]),
     "dsrg_engine_device_bytes": (_sz, [_vp]),
+    "dsrg_engine_set_size": (_i, [_vp, _i, _i]),
+    "dsrg_engine_get_size": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "dsrg_engine_set_host_chunk": (_i, [_vp, _i]),
     "dsrg_engine_set_lanes": (_i, [_vp, _i]),
     "dsrg_engine_take_launch_count": (_ll, [_vp]),
@@ -61,6 +64,10 @@ SIGNATURES = {
     "dsrg_constrainloss_backward_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "dsrg_prepare_image_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dsrg_prepare_image_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "dsrg_zoom_scores_dev": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
+    "dsrg_zoom_scores_host": (_i, [_vp, _vp, _i, _i, _vp, _i]),
+    "dsrg_predict_mask_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _pp, _vp, _i, _vp, _vp, _vp]),
+    "dsrg_predict_mask_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _pp, _vp, _i, _vp, _vp]),
     "dsrg_wire_pack_mask": (_i, [_vp, _vp, _sz]),
     "dsrg_wire_unpack_mask": (None, [_vp, _vp, _sz]),
     "dsrg_wire_apply_clamp_mask": (None, [_vp, _vp, _sz]),

@@ -9,7 +9,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, CrfParams, DsrgError, check  # noqa: F401
+from ._lib import (LAYOUT_NCHW, LAYOUT_NHWC, POST_SUM_SCORES, POST_ZOOM_PROBS, CrfParams, DsrgError,  # noqa: F401
+                   check)
 
 
 def crf_params(scale_factor=1.0, color_factor=13, maxiter=10):
@@ -80,6 +81,17 @@ class Engine(object):
     @property
     def device_bytes(self):
         return self._L.dsrg_engine_device_bytes(self.h)
+
+    def set_size(self, H, W):
+        """Select an image size within the capacity the engine was created with (no reallocation)."""
+        check(self._L.dsrg_engine_set_size(self.h, int(H), int(W)))
+        self.H, self.W = int(H), int(W)
+
+    @property
+    def capacity(self):
+        v = [C.c_int() for _ in range(4)]
+        check(self._L.dsrg_engine_get_size(self.h, *[C.byref(x) for x in v]))
+        return v[2].value, v[3].value
 
     def set_host_chunk(self, images):
         check(self._L.dsrg_engine_set_host_chunk(self.h, int(images)))
@@ -226,6 +238,56 @@ class Engine(object):
                                                   _hptr(probs, np.float32), _hptr(seeds, np.float32),
                                                   float(top_diff), _hptr(grad, np.float32)))
         return grad
+
+    # ---- inference post-processing (training/tools/test-ms.py, generate_train_gt.py) ----
+    def zoom_scores_host(self, scores, out=None, accumulate=False):
+        """(M,h,w) float32 blob -> (H,W,M): nd.zoom(scores.transpose(1,2,0), (H/h, W/w, 1), order=1), bit-exact."""
+        M, h, w = scores.shape
+        if out is None:
+            if accumulate:
+                raise ValueError("accumulate needs `out`")
+            out = np.empty((self.H, self.W, self.M), np.float32)
+        check(self._L.dsrg_zoom_scores_host(self.h, _hptr(scores, np.float32), h, w, _hptr(out, np.float32),
+                                            int(bool(accumulate))))
+        return out
+
+    def zoom_scores_dev(self, scores, out, accumulate=False, stream=None):
+        M, h, w = scores.shape
+        check(self._L.dsrg_zoom_scores_dev(self.h, _dptr(scores), h, w, _dptr(out), int(bool(accumulate)),
+                                           _stream(stream)))
+        return out
+
+    @staticmethod
+    def _post_args(scores, labels_sel):
+        n = len(scores)
+        hs = (C.c_int * n)(*[int(a.shape[1]) for a in scores])
+        ws = (C.c_int * n)(*[int(a.shape[2]) for a in scores])
+        sel = np.ascontiguousarray(labels_sel if labels_sel is not None else [], np.int32)
+        return n, hs, ws, sel
+
+    def predict_mask_host(self, scores, image, params=None, mode=POST_SUM_SCORES, eps=0.00001, smooth=True,
+                          labels_sel=None, want_probs=False):
+        """scores: list of (M,h,w) float32 blobs; image (H,W,3) uint8 -> (H,W) int32 label map
+        [, (H,W,M) float32 probabilities]."""
+        n, hs, ws, sel = self._post_args(scores, labels_sel)
+        ptrs = (C.c_void_p * n)(*[_hptr(a, np.float32).value for a in scores])
+        result = np.empty((self.H, self.W), np.int32)
+        probs = np.empty((self.H, self.W, self.M), np.float32) if want_probs else None
+        params = params if params is not None else crf_params()
+        check(self._L.dsrg_predict_mask_host(self.h, int(mode), n, ptrs, hs, ws, _hptr(image, np.uint8), float(eps),
+                                             int(bool(smooth)), C.byref(params), _hptr(sel, np.int32), int(sel.size),
+                                             _hptr(result, np.int32), _hptr(probs, np.float32)))
+        return (result, probs) if want_probs else result
+
+    def predict_mask_dev(self, scores, image, result_out, params=None, mode=POST_SUM_SCORES, eps=0.00001,
+                         smooth=True, labels_sel=None, probs_out=None, stream=None):
+        n, hs, ws, sel = self._post_args(scores, labels_sel)
+        ptrs = (C.c_void_p * n)(*[_dptr(a).value for a in scores])
+        params = params if params is not None else crf_params()
+        check(self._L.dsrg_predict_mask_dev(self.h, int(mode), n, ptrs, hs, ws, _dptr(image), float(eps),
+                                            int(bool(smooth)), C.byref(params), _hptr(sel, np.int32), int(sel.size),
+                                            _dptr(result_out), _dptr(probs_out), _stream(stream)))
+        return result_out
 
     # ---- per-kernel timing ----
     def profile(self, enable):

@@ -57,16 +57,35 @@ static bool key_range_ok(const Lattice &L, int W, int H) {
     return bound < (double)((1 << (bits - 1)) - 1) && isfinite(bound);
 }
 
+// shape-dependent strides of a lattice family; every one of them grows with N, so buffers sized for
+// the engine's capacity shape hold any smaller shape (dsrg_engine_set_size)
+static void lattice_shape(Engine *e, Lattice &L) {
+    L.N = e->N;
+    L.P = (4 - (e->N % 4)) % 4;
+    L.capv = (L.N + L.P) * (L.d + 1);
+    L.cap = 2 * L.capv;
+    L.rows_cap = (long long)e->maxB * (L.capv + 1);
+    L.nbr_stride = L.shared ? (long long)L.capv + 1 : L.rows_cap;
+}
+
+static void engine_shape(Engine *e, int H, int W) {
+    e->H = H;
+    e->W = W;
+    e->N = H * W;
+    e->tiles_x = (W + kTileW - 1) / kTileW;
+    e->tile_w = (W + e->tiles_x - 1) / e->tiles_x;  // e.g. W=321: 11 tiles of 30 instead of 10 x 32 + a 1-pixel sliver
+    e->tiles_y = (H + kTileH - 1) / kTileH;
+    e->ntiles = e->tiles_x * e->tiles_y;
+    lattice_shape(e, e->sp);
+    lattice_shape(e, e->bi);
+    e->sp_valid = false;
+}
+
 static int lattice_alloc(Engine *e, Lattice &L, int d, int shared) {
     L.d = d;
     L.shared = shared;
     L.nimg = shared ? 1 : e->maxB;
-    L.N = e->N;
-    L.P = (4 - (e->N % 4)) % 4;
-    L.capv = (L.N + L.P) * (d + 1);
-    L.cap = 2 * L.capv;
-    L.rows_cap = (long long)e->maxB * (L.capv + 1);
-    L.nbr_stride = shared ? (long long)L.capv + 1 : L.rows_cap;
+    lattice_shape(e, L);
     const size_t n = (size_t)L.nimg;
     int rc = 0;
     rc |= dalloc(e, &L.off, n * (d + 1) * L.N);
@@ -182,16 +201,21 @@ static int crf_core(Engine *e, int B, const float *unary, int layout, bool clamp
     return meanfield_run(e, B, unary, layout, clamp, unary_rw, *p, s);
 }
 
+int crf_core_for_post(Engine *e, const float *unary_hwc, const uint8_t *image, const dsrg_crf_params *p,
+                      cudaStream_t s) {
+    return crf_core(e, 1, unary_hwc, DSRG_LAYOUT_NHWC, false, nullptr, image, p, s);
+}
+
 int ensure_staging(Engine *e) {
     if (e->st_unary) return DSRG_OK;
-    const size_t n = (size_t)e->maxB * e->M * e->N;
+    const size_t n = (size_t)e->maxB * e->M * e->Ncap;
     int rc = 0;
     rc |= dalloc(e, &e->st_unary, n);
     rc |= dalloc(e, &e->st_out, n);
     rc |= dalloc(e, &e->st_cues, n);
     rc |= dalloc(e, &e->st_labels, (size_t)e->maxB * e->M);
-    rc |= dalloc(e, &e->st_image, (size_t)e->maxB * e->N * 3);
-    rc |= dalloc(e, &e->st_lmap, (size_t)e->maxB * e->N);
+    rc |= dalloc(e, &e->st_image, (size_t)e->maxB * e->Ncap * 3);
+    rc |= dalloc(e, &e->st_lmap, (size_t)e->maxB * e->Ncap);
     return rc ? DSRG_E_NOMEM : DSRG_OK;
 }
 
@@ -266,16 +290,16 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     if (!e) return nullptr;
     e->device = device;
     e->maxB = max_batch;
-    e->H = H;
-    e->W = W;
     e->M = M;
     e->MP = (M + 3) / 4 * 4;
-    e->N = H * W;
     e->sm_count = prop.multiProcessorCount;
-    e->tiles_x = (W + kTileW - 1) / kTileW;
-    e->tile_w = (W + e->tiles_x - 1) / e->tiles_x;  // e.g. W=321: 11 tiles of 30 instead of 10 x 32 + a 1-pixel sliver
-    e->tiles_y = (H + kTileH - 1) / kTileH;
-    e->ntiles = e->tiles_x * e->tiles_y;
+    e->sp.d = 2;
+    e->sp.shared = 1;
+    e->bi.d = 5;
+    e->Hcap = H;
+    e->Wcap = W;
+    e->Ncap = H * W;
+    engine_shape(e, H, W);
     int rc = 0;
     rc |= lattice_alloc(e, e->sp, 2, 1);
     rc |= lattice_alloc(e, e->bi, 5, 0);
@@ -346,6 +370,38 @@ void dsrg_engine_destroy(dsrg_engine *h) {
 
 size_t dsrg_engine_device_bytes(const dsrg_engine *h) { return h ? ((const Engine *)h)->bytes : 0; }
 
+int dsrg_engine_set_size(dsrg_engine *h, int H, int W) {
+    Engine *e = (Engine *)h;
+    if (!e) {
+        set_error("engine is NULL");
+        return DSRG_E_INVALID;
+    }
+    if (H < 1 || W < 1 || H > e->Hcap || W > e->Wcap) {
+        set_error("size %dx%d outside the engine's capacity %dx%d", H, W, e->Hcap, e->Wcap);
+        return DSRG_E_INVALID;
+    }
+    if (H == e->H && W == e->W) return DSRG_OK;
+    // work already queued keeps the old strides in its launch arguments; wait for it before the
+    // buffers are re-interpreted with the new ones
+    DSRG_CUDA_TRY(cudaSetDevice(e->device));
+    DSRG_CUDA_TRY(cudaDeviceSynchronize());
+    engine_shape(e, H, W);
+    return DSRG_OK;
+}
+
+int dsrg_engine_get_size(const dsrg_engine *h, int *H, int *W, int *Hcap, int *Wcap) {
+    const Engine *e = (const Engine *)h;
+    if (!e) {
+        set_error("engine is NULL");
+        return DSRG_E_INVALID;
+    }
+    if (H) *H = e->H;
+    if (W) *W = e->W;
+    if (Hcap) *Hcap = e->Hcap;
+    if (Wcap) *Wcap = e->Wcap;
+    return DSRG_OK;
+}
+
 long long dsrg_engine_take_launch_count(dsrg_engine *h) {
     Engine *e = (Engine *)h;
     if (!e) return 0;
@@ -357,7 +413,7 @@ long long dsrg_engine_take_launch_count(dsrg_engine *h) {
 static const char *kTagNames[T_COUNT] = {
     "lattice_insert", "lattice_misc", "lattice_norm", "mf_init", "mf_zero", "mf_blur_spatial",
     "mf_blur_bilateral", "mf_tile", "mf_export", "srg_label", "srg_merge", "srg_flag", "srg_emit",
-    "seedloss", "wire_bits", "prepare_image"};
+    "seedloss", "wire_bits", "prepare_image", "postprocess"};
 
 int dsrg_profile_tag_count(void) { return T_COUNT; }
 

@@ -72,7 +72,7 @@ struct Engine;
 enum KTag {
     T_LAT_INSERT = 0, T_LAT_MISC, T_LAT_NORM, T_MF_INIT, T_MF_ZERO, T_MF_BLUR_SP,
     T_MF_BLUR_BI, T_MF_TILE, T_MF_EXPORT, T_SRG_LABEL, T_SRG_MERGE, T_SRG_FLAG, T_SRG_EMIT,
-    T_LOSS, T_WIRE, T_PREP, T_COUNT
+    T_LOSS, T_WIRE, T_PREP, T_POST, T_COUNT
 };
 
 // ---- lattice.cu ----
@@ -110,6 +110,7 @@ int seedloss_backward(Engine *e, int B, int n_global, const float *probs, const 
 struct Engine {
     int device = 0;
     int maxB = 0, H = 0, W = 0, M = 0, MP = 0, N = 0;
+    int Hcap = 0, Wcap = 0, Ncap = 0;  // shape the buffers were sized for (H <= Hcap, W <= Wcap)
     int sm_count = 148;
     size_t bytes = 0;
     long long launches = 0;

@@ -4,12 +4,10 @@
 // (CRF/krahenbuhl2013/CRF.py:32).  At the training shape scipy's zoom alone costs ~13 ms per batch on
 // the host, an order of magnitude more than the whole GPU pass.
 //
-// scipy.ndimage.zoom(order=1, grid_mode=False) maps output index o to input coordinate
-// o * (in-1)/(out-1) and interpolates linearly in float64; the restatement below (validated
-// bit-for-bit against scipy in tests/test_oracle_golden.py) keeps scipy's operation order:
-//   t = v00*(wy0*wx0) + v01*(wy0*wx1) + v10*(wy1*wx0) + v11*(wy1*wx1), all float64, no contraction,
-// cast to float32 (the blob dtype), + mean in float64, round half to even, C cast to unsigned char.
+// The zoom follows scipy.ndimage.zoom(order=1) operation by operation (zoom.cuh); the result is cast to
+// float32 (the blob dtype), + mean in float64, round half to even, C cast to unsigned char.
 #include "common.cuh"
+#include "zoom.cuh"
 
 namespace dsrg {
 
@@ -20,24 +18,11 @@ k_prepare_image(const float *in, uint8_t *out, int Hi, int Wi, int Ho, int Wo, d
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ho * Wo) return;
     const int oy = i / Wo, ox = i - oy * Wo;
-    const double zy = Ho > 1 ? (double)(Hi - 1) / (double)(Ho - 1) : 0.0;
-    const double zx = Wo > 1 ? (double)(Wi - 1) / (double)(Wo - 1) : 0.0;
-    const double ys = __dmul_rn((double)oy, zy), xs = __dmul_rn((double)ox, zx);
-    const int y0 = (int)floor(ys), x0 = (int)floor(xs);
-    const double fy = __dsub_rn(ys, (double)y0), fx = __dsub_rn(xs, (double)x0);
-    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
-    const double wy0 = __dsub_rn(1.0, fy), wx0 = __dsub_rn(1.0, fx);
-    const double w00 = __dmul_rn(wy0, wx0), w01 = __dmul_rn(wy0, fx), w10 = __dmul_rn(fy, wx0),
-                 w11 = __dmul_rn(fy, fx);
+    const ZoomTap tap = zoom_tap(oy, ox, Hi, Wi, Ho, Wo);
     const double mean[3] = {m0, m1, m2};
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const float *p = in + ((size_t)b * 3 + c) * Hi * Wi;
-        double t = __dmul_rn((double)p[(size_t)y0 * Wi + x0], w00);
-        t = __dadd_rn(t, __dmul_rn((double)p[(size_t)y0 * Wi + x1], w01));
-        t = __dadd_rn(t, __dmul_rn((double)p[(size_t)y1 * Wi + x0], w10));
-        t = __dadd_rn(t, __dmul_rn((double)p[(size_t)y1 * Wi + x1], w11));
-        const float z = (float)t;                              // zoom returns the input dtype (float32)
+        const float z = zoom_apply(in + ((size_t)b * 3 + c) * Hi * Wi, Wi, tap);  // float32 like the blob
         const double r = rint(__dadd_rn((double)z, mean[c]));  // + mean_pixel (float64), np.round
         out[((size_t)b * Ho * Wo + i) * 3 + c] = (uint8_t)(long long)r;  // .astype('ubyte')
     }

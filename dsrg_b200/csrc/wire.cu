@@ -183,7 +183,7 @@ static void unpack_planes(const uint32_t *sbits, float *seeds, const uint32_t *m
 
 static int ensure_wire(Engine *e) {
     if (e->d_cbits) return DSRG_OK;
-    const size_t wpi = ((size_t)e->M * e->N + 31) / 32, n = (size_t)e->maxB * wpi;
+    const size_t wpi = ((size_t)e->M * e->Ncap + 31) / 32, n = (size_t)e->maxB * wpi;
     int rc = 0;
     rc |= dalloc(e, &e->d_cbits, n);
     rc |= dalloc(e, &e->d_sbits, n);

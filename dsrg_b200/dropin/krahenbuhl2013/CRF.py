@@ -1,27 +1,12 @@
 """Drop-in for CRF/krahenbuhl2013/CRF.py: same function name, arguments, defaults and return value,
 computed by the batched B200 engine (a batch of one) instead of a per-call CPU DenseCRFWrapper."""
-import collections
-
 import numpy as np
 
 from dsrg_b200 import api as _api
+from dsrg_b200.pool import engine_for as _engine
 from krahenbuhl2013.wrapper import DenseCRF  # noqa: F401  (re-exported like the reference module)
 
 __all__ = ["CRF", "DenseCRF"]
-
-_ENGINES = collections.OrderedDict()   # (H, W, M) -> Engine, least recently used first
-_MAX_ENGINES = 4                       # test scripts feed images of many sizes; keep a few resident
-
-
-def _engine(H, W, M):
-    key = (int(H), int(W), int(M))
-    eng = _ENGINES.pop(key, None)
-    if eng is None:
-        while len(_ENGINES) >= _MAX_ENGINES:
-            _ENGINES.popitem(last=False)[1].close()
-        eng = _api.Engine(1, key[0], key[1], key[2])
-    _ENGINES[key] = eng
-    return eng
 
 
 def CRF(image, unary, maxiter=10, scale_factor=1.0, color_factor=13):

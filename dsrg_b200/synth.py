@@ -88,3 +88,22 @@ def make_batch(B, H, W, C=C_DEFAULT, cues="cam", image="smooth", seed=1234, star
                 probs=np.stack([p["probs"] for p in pick]),
                 cues=np.stack([p["cues"] for p in pick]),
                 image=np.stack([p["image"] for p in pick]))
+
+
+def make_score_blobs(index, H, W, sizes=(31, 41, 51), C=C_DEFAULT, image="smooth", seed=4321):
+    """Inputs of the inference post-processing (training/tools/test-ms.py:84-111): one (C,h,w) float32
+    score blob per network scale -- the same blobby scene seen at every scale plus independent noise --
+    the (H,W,3) uint8 image and the image tags (class ids without background)."""
+    rng = np.random.RandomState(seed + index)
+    labels = make_labels(rng, C)
+    centres = [(c, rng.uniform(0, 1), rng.uniform(0, 1)) for c in np.where(labels == 1)[0]]
+    blobs = []
+    for s in sizes:
+        ys, xs = np.mgrid[0:s, 0:s] / float(max(s - 1, 1))
+        sc = rng.randn(C, s, s)
+        for c, cy, cx in centres:
+            sc[c] += 6.0 * np.exp(-0.5 * (((ys - cy) / 0.25) ** 2 + ((xs - cx) / 0.25) ** 2))
+        blobs.append(sc.astype(np.float32))
+    im = make_image(rng, H, W, image)
+    tags = np.where(labels[1:] == 1)[0] + 1
+    return dict(blobs=blobs, image=im, tags=tags)

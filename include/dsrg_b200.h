@@ -74,6 +74,11 @@ typedef struct dsrg_engine dsrg_engine;
 dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M);
 void dsrg_engine_destroy(dsrg_engine *e);
 size_t dsrg_engine_device_bytes(const dsrg_engine *e); /* bytes of HBM held by the engine */
+/* The H x W given to dsrg_engine_create is a capacity: any H' <= H, W' <= W can be selected afterwards
+ * without reallocating (the evaluation tools run one image at a time, each of its own size --
+ * training/tools/test-ms.py:86-87).  Waits for queued work; the cached spatial lattice is rebuilt. */
+int dsrg_engine_set_size(dsrg_engine *e, int H, int W);
+int dsrg_engine_get_size(const dsrg_engine *e, int *H, int *W, int *H_capacity, int *W_capacity);
 /* The *_host full-pass entry points pipeline the batch in chunks (default B/8, 3B/8, B/2 images) through
  * H2D | kernels | D2H streams; `images` > 0 caps the chunk size, 0 restores the default. */
 int dsrg_engine_set_host_chunk(dsrg_engine *e, int images);
@@ -177,6 +182,38 @@ int dsrg_prepare_image_dev(dsrg_engine *e, int B, int Hi, int Wi, const float *i
                            const double *mean_pixel /* host, 3 */, uint8_t *image_out_dev, void *stream);
 int dsrg_prepare_image_host(dsrg_engine *e, int B, int Hi, int Wi, const float *images_host,
                             const double *mean_pixel /* host, 3 */, uint8_t *image_out_host);
+
+/*
+ * Full-resolution inference post-processing: what predict_mask() of the evaluation / ground-truth tools
+ * does between the network's score blob and the label map (engine batch 1, size = the image's):
+ *   DSRG_POST_SUM_SCORES  training/tools/test-ms.py:84-111: scores_all = sum_k zoom(scores_k, order=1);
+ *                         softmax over labels; clamp at eps; CRF(im, log(probs)); argmax
+ *   DSRG_POST_ZOOM_PROBS  training/tools/generate_train_gt.py:76-104: softmax at network resolution;
+ *                         zoom(probs, order=1); clamp at eps; CRF(im, log(probs)); argmax over `labels_sel`
+ *   scores     : n_scales pointers to [M][h_k][w_k] float32 (net.blobs['fc8-SEC'].data[0]); the array of
+ *                pointers and hs / ws live on the host in both variants
+ *   image      : [H][W][3] uint8 as handed to krahenbuhl2013.CRF (may be NULL when smooth == 0)
+ *   smooth     : 0 skips the CRF (the tools' `smooth=False`)
+ *   labels_sel : n_sel label ids ([0] + image tags in generate_train_gt.py:96-97); n_sel == 0 = all labels
+ *   result_out : [H][W] int32 label map;  probs_out : optional [H][W][M] float32 (CRF marginals, or the
+ *                clamped probabilities when smooth == 0)
+ * dsrg_zoom_scores_* is the zoom step alone ([M][h][w] -> [H][W][M], scipy.ndimage.zoom order=1 semantics,
+ * bit-exact; accumulate != 0 adds to `out` in float32 like `scores_all += scores`).
+ */
+#define DSRG_POST_SUM_SCORES 0
+#define DSRG_POST_ZOOM_PROBS 1
+int dsrg_zoom_scores_dev(dsrg_engine *e, const float *scores_dev, int h, int w, float *out_dev, int accumulate,
+                         void *stream);
+int dsrg_zoom_scores_host(dsrg_engine *e, const float *scores_host, int h, int w, float *out_host,
+                          int accumulate);
+int dsrg_predict_mask_dev(dsrg_engine *e, int mode, int n_scales, const float *const *scores_dev, const int *hs,
+                          const int *ws, const uint8_t *image_dev, float eps, int smooth,
+                          const dsrg_crf_params *params, const int32_t *labels_sel, int n_sel,
+                          int32_t *result_out_dev, float *probs_out_dev, void *stream);
+int dsrg_predict_mask_host(dsrg_engine *e, int mode, int n_scales, const float *const *scores_host,
+                           const int *hs, const int *ws, const uint8_t *image_host, float eps, int smooth,
+                           const dsrg_crf_params *params, const int32_t *labels_sel, int n_sel,
+                           int32_t *result_out_host, float *probs_out_host);
 
 /* Host-only helpers of the *_host wire format (0/1 planes cross PCIe as 1 bit per value, see
  * csrc/wire.cu); exported for unit tests.  pack returns 1 if every value was exactly 0 or 1. */

@@ -243,23 +243,35 @@ def prepare_image(im, h, w):
 
 def zoom_order1_restated(im, oh, ow):
     """scipy.ndimage.zoom(im, (1, 1, oh/H, ow/W), order=1) for a (N,C,H,W) float32 array, restated
-    operation by operation (float64 arithmetic, scipy's tap order); tests check it bit-for-bit against
-    scipy and the CUDA kernel against it."""
+    operation by operation; tests check it bit-for-bit against scipy and the CUDA kernels against it.
+    scipy's arithmetic (ni_interpolation.c NI_ZoomShift, ni_splines.c), all float64:
+      * output index o maps to c = o * ((in-1)/(out-1)); c > in-1 (possible by one rounding error at the
+        last row / column) is out of bounds under the default mode='constant' -> the pixel is cval = 0
+      * weights w0 = 1 - (c - floor(c)), w1 = 1 - w0   (NOT c - floor(c))
+      * each tap is ((v * wy) * wx), taps summed in the order (y0,x0), (y0,x1), (y1,x0), (y1,x1)
+      * the sum is cast to the input dtype
+    """
     n, c, ih, iw = im.shape
     zy = (ih - 1) / (oh - 1) if oh > 1 else 0.0
     zx = (iw - 1) / (ow - 1) if ow > 1 else 0.0
     ys = np.arange(oh, dtype=np.float64) * zy
     xs = np.arange(ow, dtype=np.float64) * zx
-    y0 = np.floor(ys).astype(int)
-    x0 = np.floor(xs).astype(int)
-    fy, fx = ys - y0, xs - x0
+    oob = (ys[:, None] > ih - 1) | (xs[None, :] > iw - 1)
+    y0 = np.minimum(np.floor(ys).astype(int), ih - 1)
+    x0 = np.minimum(np.floor(xs).astype(int), iw - 1)
+    wy0, wx0 = 1 - (ys - y0), 1 - (xs - x0)
+    wy1, wx1 = 1 - wy0, 1 - wx0
     y1, x1 = np.minimum(y0 + 1, ih - 1), np.minimum(x0 + 1, iw - 1)
     a = im.astype(np.float64)
-    wy0, wx0 = 1 - fy, 1 - fx
-    t = a[:, :, y0][:, :, :, x0] * (wy0[:, None] * wx0[None, :])
-    t = t + a[:, :, y0][:, :, :, x1] * (wy0[:, None] * fx[None, :])
-    t = t + a[:, :, y1][:, :, :, x0] * (fy[:, None] * wx0[None, :])
-    t = t + a[:, :, y1][:, :, :, x1] * (fy[:, None] * fx[None, :])
+
+    def tap(yy, xx, wy, wx):
+        return (a[:, :, yy][:, :, :, xx] * wy[:, None]) * wx[None, :]
+
+    t = tap(y0, x0, wy0, wx0)
+    t = t + tap(y0, x1, wy0, wx1)
+    t = t + tap(y1, x0, wy1, wx0)
+    t = t + tap(y1, x1, wy1, wx1)
+    t[:, :, oob] = 0.0
     return t.astype(im.dtype)
 
 

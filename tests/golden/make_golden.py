@@ -24,7 +24,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from dsrg_b200 import synth  # noqa: E402
-from oracle import crf_oracle, srg_oracle  # noqa: E402
+from oracle import crf_oracle, post_oracle, srg_oracle  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -139,9 +139,33 @@ def make_crf():
         print("crf", name, q.shape, float(q.max()))
 
 
+POST_CASES = [  # name, mode, H, W, network sizes, index
+    ("ms_48x64", "ms", 48, 64, (17, 21, 25), 20),
+    ("gt_40x56", "gt", 40, 56, (21,), 21),
+]
+
+
+def post_inputs(H, W, sizes, index):
+    s = synth.make_score_blobs(index, H, W, sizes)
+    return s["image"], s["blobs"], s["tags"]
+
+
+def make_post():
+    for name, mode, H, W, sizes, index in POST_CASES:
+        im, blobs, tags = post_inputs(H, W, sizes, index)
+        if mode == "ms":
+            lab, probs = post_oracle.predict_mask_ms(im, blobs, smooth=True)
+        else:
+            lab, probs = post_oracle.predict_mask_gt(im, blobs[0], tags, smooth=True)
+        np.savez_compressed(os.path.join(OUT, "post_oracle_%s.npz" % name), inputs_sha256=digest(im, *blobs),
+                            tags=tags, labels=lab.astype(np.uint8), probs=probs.astype(np.float32))
+        print("post", name, lab.shape, np.unique(lab))
+
+
 if __name__ == "__main__":
     assert srg_oracle.reference_available(), "needs /root/reference"
     crf_oracle.build(force=True)
     make_srg()
     make_lattice()
     make_crf()
+    make_post()

@@ -92,7 +92,8 @@ def test_generate_seed_step_function(torch_cuda):
     assert out is seed_c and np.array_equal(out, want)
 
 
-@pytest.mark.parametrize("ih,iw,h,w", [(321, 321, 41, 41), (97, 131, 33, 57), (50, 40, 50, 40), (17, 9, 40, 31)])
+@pytest.mark.parametrize("ih,iw,h,w", [(321, 321, 41, 41), (97, 131, 33, 57), (50, 40, 50, 40), (17, 9, 40, 31),
+                                       (51, 51, 60, 45)])   # last: scipy maps the final column out of bounds -> 0
 def test_prepare_image_matches_scipy_pipeline(torch_cuda, ih, iw, h, w):
     """dsrg_prepare_image (zoom order=1 + mean + round + ubyte) == the reference's scipy pipeline, byte for byte."""
     from dsrg_b200 import api

@@ -110,8 +110,44 @@ def test_zoom_restatement_is_bit_exact_vs_scipy():
     from scipy.ndimage import zoom
     rng = np.random.RandomState(4)
     for (ih, iw, oh, ow) in ((321, 321, 41, 41), (97, 131, 33, 57), (50, 40, 50, 40), (17, 9, 40, 31), (8, 8, 1, 1),
-                             (5, 7, 1, 4)):
+                             (5, 7, 1, 4), (33, 33, 321, 321), (31, 31, 97, 131), (51, 51, 60, 45)):
         im = (rng.rand(2, 3, ih, iw) * 255 - 110).astype(np.float32)
         want = zoom(im, (1.0, 1.0, float(oh) / ih, float(ow) / iw), order=1)
         got = crf_oracle.zoom_order1_restated(im, oh, ow)
         assert want.shape == got.shape and want.dtype == got.dtype and np.array_equal(want, got)
+
+
+def test_zoom_restatement_covers_score_maps():
+    """(h,w,M) score maps zoomed with a trailing identity axis (test-ms.py:96): same taps, same bits."""
+    from scipy.ndimage import zoom
+    rng = np.random.RandomState(5)
+    for (h, w, H, W) in ((41, 41, 375, 500), (31, 31, 97, 131), (51, 51, 60, 45), (41, 41, 20, 30), (7, 9, 1, 5),
+                         (33, 33, 321, 321)):
+        blob = (rng.randn(21, h, w) * 5).astype(np.float32)
+        want = zoom(np.transpose(blob, [1, 2, 0]), (float(H) / h, float(W) / w, 1.0), order=1)
+        got = crf_oracle.zoom_order1_restated(blob[None], H, W)[0].transpose(1, 2, 0)
+        assert want.shape == (H, W, 21) and np.array_equal(want, got)
+
+
+@pytest.mark.parametrize("case", make_golden.POST_CASES, ids=[c[0] for c in make_golden.POST_CASES])
+def test_post_oracle_matches_frozen_golden(case):
+    from oracle import post_oracle
+    name, mode, H, W, sizes, index = case
+    g = load_golden("post_oracle_%s.npz" % name)
+    im, blobs, tags = make_golden.post_inputs(H, W, sizes, index)
+    assert digest(im, *blobs) == str(g["inputs_sha256"])
+    if mode == "ms":
+        lab, probs = post_oracle.predict_mask_ms(im, blobs, smooth=True)
+        sel = list(range(21))
+    else:
+        lab, probs = post_oracle.predict_mask_gt(im, blobs[0], tags, smooth=True)
+        sel = [0] + list(tags)
+        assert set(np.unique(lab)) <= set(sel)
+    np.testing.assert_allclose(probs, g["probs"], atol=1e-6, rtol=0)
+    bad = lab != g["labels"]
+    if bad.any():   # another libm may flip an exact near-tie
+        top2 = np.sort(g["probs"][:, :, sel], axis=2)[:, :, -2:]
+        assert ((top2[:, :, 1] - top2[:, :, 0])[bad] < 1e-5).all()
+    # smooth=False is plain numpy: arg-max of the clamped soft-max
+    lab0, p0 = post_oracle.predict_mask_ms(im, blobs, smooth=False)
+    assert np.array_equal(lab0, p0.argmax(2)) and p0.min() >= np.float32(1e-5)
