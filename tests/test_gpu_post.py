@@ -77,7 +77,7 @@ def test_engine_set_size_full_pass_bit_exact_srg(torch_cuda):
         b = synth.make_batch(3, H, W, cues="random", image="smooth", start=H)
         seeds = eng.srg_host(b["labels"], b["probs"], b["cues"], 0.99, 0.85)
         for i in range(3):
-            want = srg_oracle.generate_seed_step(b["labels"][i], b["cues"][i], b["probs"][i].astype(np.float64), 0.99, 0.85)
+            want = srg_oracle.srg_closed_form(b["labels"][i], b["cues"][i], b["probs"][i], 0.99, 0.85)
             assert np.array_equal(seeds[i], want)
     eng.close()
 
