@@ -68,6 +68,8 @@ SIGNATURES = {
     "dsrg_zoom_scores_host": (_i, [_vp, _vp, _i, _i, _vp, _i]),
     "dsrg_predict_mask_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _pp, _vp, _i, _vp, _vp, _vp]),
     "dsrg_predict_mask_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _pp, _vp, _i, _vp, _vp]),
+    "dsrg_annotation_forward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "dsrg_annotation_forward_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "dsrg_wire_pack_mask": (_i, [_vp, _vp, _sz]),
     "dsrg_wire_unpack_mask": (None, [_vp, _vp, _sz]),
     "dsrg_wire_apply_clamp_mask": (None, [_vp, _vp, _sz]),

@@ -289,6 +289,45 @@ class Engine(object):
                                             _dptr(result_out), _dptr(probs_out), _stream(stream)))
         return result_out
 
+    # ---- AnnotationLayer.forward (pylayers.py:369-387) ----
+    @staticmethod
+    def _annot_args(tags, cues, flip):
+        """tags: per image 1-D class ids; cues: per image (3,K) int arrays (class,row,col) -> CSR int32."""
+        B = len(tags)
+        toff = np.zeros(B + 1, np.int32)
+        coff = np.zeros(B + 1, np.int32)
+        for i in range(B):
+            toff[i + 1] = toff[i] + np.asarray(tags[i]).size
+            coff[i + 1] = coff[i] + np.asarray(cues[i]).reshape(3, -1).shape[1]
+        tg = np.ascontiguousarray(np.concatenate([np.asarray(t).reshape(-1) for t in tags]) if toff[B] else [], np.int32)
+        ci = np.ascontiguousarray(np.concatenate([np.asarray(c).reshape(3, -1) for c in cues], axis=1) if coff[B]
+                                  else np.zeros((3, 0)), np.int32)
+        fl = None if flip is None else np.ascontiguousarray(flip, np.int32)
+        return B, toff, tg, coff, ci, fl
+
+    def annotation_forward_host(self, tags, cues, flip=None, images=None):
+        """-> labels (B,1,1,M), cues (B,M,H,W)[, images (B,3,Hi,Wi)] float32."""
+        B, toff, tg, coff, ci, fl = self._annot_args(tags, cues, flip)
+        labels = np.empty((B, 1, 1, self.M), np.float32)
+        dense = np.empty((B, self.M, self.H, self.W), np.float32)
+        out_im = None if images is None else np.empty(images.shape, np.float32)
+        Hi, Wi = (0, 0) if images is None else images.shape[2:]
+        check(self._L.dsrg_annotation_forward_host(self.h, B, _hptr(toff, np.int32), _hptr(tg, np.int32),
+                                                   _hptr(coff, np.int32), _hptr(ci, np.int32), _hptr(fl, np.int32),
+                                                   _hptr(images, np.float32), Hi, Wi, _hptr(labels, np.float32),
+                                                   _hptr(dense, np.float32), _hptr(out_im, np.float32)))
+        return (labels, dense) if images is None else (labels, dense, out_im)
+
+    def annotation_forward_dev(self, tags, cues, labels_out, cues_out, flip=None, images=None, images_out=None,
+                               stream=None):
+        B, toff, tg, coff, ci, fl = self._annot_args(tags, cues, flip)
+        Hi, Wi = (0, 0) if images is None else images.shape[2:]
+        check(self._L.dsrg_annotation_forward_dev(self.h, B, _hptr(toff, np.int32), _hptr(tg, np.int32),
+                                                  _hptr(coff, np.int32), _hptr(ci, np.int32), _hptr(fl, np.int32),
+                                                  _dptr(images), Hi, Wi, _dptr(labels_out), _dptr(cues_out),
+                                                  _dptr(images_out), _stream(stream)))
+        return labels_out, cues_out
+
     # ---- per-kernel timing ----
     def profile(self, enable):
         check(self._L.dsrg_engine_profile(self.h, int(bool(enable))))

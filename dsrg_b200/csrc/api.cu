@@ -350,7 +350,7 @@ void dsrg_engine_destroy(dsrg_engine *h) {
     lattice_free(e->bi);
     void *ptrs[] = {e->U, e->Q0, e->spA, e->spB, e->spC, e->biA, e->biB, e->biC, e->nvA, e->nvB, e->lmap,
                     e->lflag, e->parent, e->hc, e->loss_acc, e->dev_err, e->st_unary, e->st_out,
-                    e->st_cues, e->st_labels, e->st_image, e->st_lmap, e->st_raw};
+                    e->st_cues, e->st_labels, e->st_image, e->st_lmap, e->st_raw, e->st_idx};
     for (void *p : ptrs) cudaFree(p);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->in_stream) cudaStreamDestroy(e->in_stream);
@@ -413,7 +413,7 @@ long long dsrg_engine_take_launch_count(dsrg_engine *h) {
 static const char *kTagNames[T_COUNT] = {
     "lattice_insert", "lattice_misc", "lattice_norm", "mf_init", "mf_zero", "mf_blur_spatial",
     "mf_blur_bilateral", "mf_tile", "mf_export", "srg_label", "srg_merge", "srg_flag", "srg_emit",
-    "seedloss", "wire_bits", "prepare_image", "postprocess"};
+    "seedloss", "wire_bits", "prepare_image", "postprocess", "annotation"};
 
 int dsrg_profile_tag_count(void) { return T_COUNT; }
 

@@ -72,7 +72,7 @@ struct Engine;
 enum KTag {
     T_LAT_INSERT = 0, T_LAT_MISC, T_LAT_NORM, T_MF_INIT, T_MF_ZERO, T_MF_BLUR_SP,
     T_MF_BLUR_BI, T_MF_TILE, T_MF_EXPORT, T_SRG_LABEL, T_SRG_MERGE, T_SRG_FLAG, T_SRG_EMIT,
-    T_LOSS, T_WIRE, T_PREP, T_POST, T_COUNT
+    T_LOSS, T_WIRE, T_PREP, T_POST, T_ANNOT, T_COUNT
 };
 
 // ---- lattice.cu ----
@@ -139,6 +139,8 @@ struct Engine {
     uint8_t *st_image = nullptr;
     float *st_raw = nullptr;   // raw (un-zoomed) images of the *_host preprocessing entry point
     size_t st_raw_cap = 0;
+    int32_t *st_idx = nullptr;  // index lists of the annotation entry points
+    size_t st_idx_cap = 0;
     int32_t *st_lmap = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr, aux_stream = nullptr;
     cudaEvent_t fork_event = nullptr, join_event = nullptr;

@@ -201,3 +201,58 @@ class DSRGLayer(caffe.Layer):
                                       _api.crf_params(12.0), self._th1, self._th2)
         _clamped_writeback(probs, p)
         return seeds
+
+
+class AnnotationLayer(caffe.Layer):
+    """pylayers.py:346-387 -> dsrg_annotation_forward_host.  The pickle of localisation cues is read on
+    the host like the reference does (cPickle -> pickle, latin1 for the Python-2 file); `np.random.choice`
+    is drawn per image in the reference's order, so a seeded run mirrors the same images.
+    ``param_str`` keys: `cues` (file name, default 'localization_cues.pickle'), `mirror`; additionally
+    `root` (directory of the cue files; default: the reference's ../../training/localization_cues
+    relative to this module, or $DSRG_CUES_DIR)."""
+
+    def setup(self, bottom, top):
+        import os
+        import os.path as osp
+        import pickle
+        if len(bottom) != 2:
+            raise Exception("The layer needs two inputs!")
+
+        layer_params = yaml.safe_load(self.param_str)
+        if 'cues' not in layer_params:
+            layer_params['cues'] = 'localization_cues.pickle'
+        self._cue_name = layer_params['cues']
+
+        if 'mirror' not in layer_params:
+            layer_params['mirror'] = False
+        self.is_mirror = layer_params['mirror']
+
+        this_dir = osp.dirname(__file__)
+        root = layer_params.get('root') or os.environ.get('DSRG_CUES_DIR') or \
+            osp.join(this_dir, '../../training', 'localization_cues')
+        with open(osp.join(root, self._cue_name), 'rb') as f:
+            self.data_file = pickle.load(f, encoding='latin1')
+
+    def reshape(self, bottom, top):
+        top[0].reshape(bottom[0].data.shape[0], 1, 1, 21)
+        top[1].reshape(bottom[0].data.shape[0], 21, 41, 41)
+        top[2].reshape(*bottom[1].data.shape)
+
+    def forward(self, bottom, top):
+        ids = np.asarray(bottom[0].data[...]).reshape(-1)
+        tags, cues, flips = [], [], []
+        for image_id in ids:
+            tags.append(self.data_file['%i_labels' % image_id])
+            cues.append(self.data_file['%i_cues' % image_id])
+            if self.is_mirror:
+                flips.append(int(np.random.choice(2) * 2 - 1 == -1))      # pylayers.py:385
+        n = len(ids)
+        eng = _engine(n, 21, 41, 41)
+        labels, dense, images = eng.annotation_forward_host(tags, cues, flips if self.is_mirror else None,
+                                                            _f32(bottom[1].data))
+        top[0].data[...] = labels
+        top[1].data[...] = dense
+        top[2].data[...] = images
+
+    def backward(self, top, propagate_down, bottom):
+        pass

@@ -215,6 +215,26 @@ int dsrg_predict_mask_host(dsrg_engine *e, int mode, int n_scales, const float *
                            const dsrg_crf_params *params, const int32_t *labels_sel, int n_sel,
                            int32_t *result_out_host, float *probs_out_host);
 
+/*
+ * AnnotationLayer.forward (pylayers/pylayers/pylayers.py:369-387): image tags + sparse localisation cues
+ * -> the dense `labels` [B][1][1][M] and `cues` [B][M][H][W] blobs (H x W = the engine's size), and the
+ * optionally mirrored copy of the images.  Reading the pickle and drawing `flip` stay with the caller:
+ *   tag_offsets [B+1], tags       : CSR of data_file['%i_labels'] per image (class ids; label 0 is always set)
+ *   cue_offsets [B+1], cue_idx    : CSR of data_file['%i_cues']; cue_idx is [3][K] (class, row, column rows,
+ *                                   K = cue_offsets[B]); negative indices wrap like numpy's, others are errors
+ *   flip [B] or NULL              : 1 = mirror this image's cues and pixels along the width (flip == -1, :385)
+ *   images_in / images_out        : [B][3][Hi][Wi] float32, distinct buffers; both NULL = skip the copy
+ * All index arrays live on the host in both variants.
+ */
+int dsrg_annotation_forward_dev(dsrg_engine *e, int B, const int32_t *tag_offsets, const int32_t *tags,
+                                const int32_t *cue_offsets, const int32_t *cue_idx, const int32_t *flip,
+                                const float *images_in_dev, int Hi, int Wi, float *labels_out_dev,
+                                float *cues_out_dev, float *images_out_dev, void *stream);
+int dsrg_annotation_forward_host(dsrg_engine *e, int B, const int32_t *tag_offsets, const int32_t *tags,
+                                 const int32_t *cue_offsets, const int32_t *cue_idx, const int32_t *flip,
+                                 const float *images_in_host, int Hi, int Wi, float *labels_out_host,
+                                 float *cues_out_host, float *images_out_host);
+
 /* Host-only helpers of the *_host wire format (0/1 planes cross PCIe as 1 bit per value, see
  * csrc/wire.cu); exported for unit tests.  pack returns 1 if every value was exactly 0 or 1. */
 int dsrg_wire_pack_mask(const float *src_host, uint32_t *dst_bits, size_t n);
