@@ -413,7 +413,7 @@ long long dsrg_engine_take_launch_count(dsrg_engine *h) {
 static const char *kTagNames[T_COUNT] = {
     "lattice_insert", "lattice_misc", "lattice_norm", "mf_init", "mf_zero", "mf_blur_spatial",
     "mf_blur_bilateral", "mf_tile", "mf_export", "srg_label", "srg_merge", "srg_flag", "srg_emit",
-    "seedloss", "wire_bits", "prepare_image", "postprocess", "annotation"};
+    "seedloss", "wire_bits", "prepare_image", "postprocess", "annotation", "mf_blur_fused"};
 
 int dsrg_profile_tag_count(void) { return T_COUNT; }
 

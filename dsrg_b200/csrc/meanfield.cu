@@ -8,7 +8,12 @@
 // State is planar: U, Q are [B][M][N] float32 (one coalesced load per label per thread);
 // lattice value rows are [rows][MP] float32 with MP = M rounded up to a multiple of 4
 // (the reference pads 21 -> 24 the same way, permutohedral.cpp:531).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dsrg {
 
@@ -395,9 +400,8 @@ k_mf_zero(float4 *a, const int32_t *rowbase_a, float4 *c, const int32_t *rowbase
 // one thread per (row, float4 chunk), rows of images [b0, b0+nb)
 // ---------------------------------------------------------------------------------------------
 template <int MP>
-__global__ void __launch_bounds__(kThreads)
-k_mf_blur(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase, int b0, int nb, int shared,
-          float4 *zero) {
+__device__ __forceinline__ void blur_pass(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase,
+                                          int b0, int nb, int shared, float4 *zero) {
     constexpr int CH = MP / 4;
     const long long r0 = rowbase[b0], rows = rowbase[b0 + nb] - r0;
     const int rows_img = shared ? rowbase[1] : 0;
@@ -428,6 +432,46 @@ k_mf_blur(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase
         // the buffer that was sliced in this iteration is dead by now: clear it here so that it can be
         // the next splat target without a separate zeroing pass
         if (zero) zero[g * CH + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int MP>
+__global__ void __launch_bounds__(kThreads)
+k_mf_blur(const float4 *in, float4 *out, const int2 *nbr, const int32_t *rowbase, int b0, int nb, int shared,
+          float4 *zero) {
+    blur_pass<MP>(in, out, nbr, rowbase, b0, nb, shared, zero);
+}
+
+// All d+1 axes of both lattices in ONE cooperative launch: phase j blurs axis j of the bilateral lattice and
+// (j <= 2) of the spatial one, a grid-wide barrier separates the phases.  Replaces 9 dependent launches per
+// mean-field iteration; at small batches those launches are pure latency (7-8 us each for ~1 us of work).
+// Off by default (DSRG_B200_FUSED_BLUR=1 enables it), see fused_blur_grid() for the measurements.
+struct BlurLat {
+    const int2 *nbr;
+    long long nbr_stride;
+    const int32_t *rowbase;
+    float4 *buf, *tmp, *dead;
+    int shared, d;
+};
+
+template <int MP>
+__global__ void __launch_bounds__(kThreads, 8)
+k_mf_blur_fused(BlurLat sp, BlurLat bi, int b0, int nb) {
+    cg::grid_group grid = cg::this_grid();
+    float4 *ssrc = sp.buf, *sdst = sp.tmp, *bsrc = bi.buf, *bdst = bi.tmp;
+    const int phases = max(sp.d, bi.d) + 1;
+    for (int j = 0; j < phases; j++) {
+        if (j <= sp.d) {
+            blur_pass<MP>(ssrc, sdst, sp.nbr + (size_t)j * sp.nbr_stride, sp.rowbase, b0, nb, sp.shared,
+                          j == 0 ? sp.dead : nullptr);
+            float4 *t = ssrc; ssrc = sdst; sdst = t;
+        }
+        if (j <= bi.d) {
+            blur_pass<MP>(bsrc, bdst, bi.nbr + (size_t)j * bi.nbr_stride, bi.rowbase, b0, nb, bi.shared,
+                          j == 0 ? bi.dead : nullptr);
+            float4 *t = bsrc; bsrc = bdst; bdst = t;
+        }
+        if (j + 1 < phases) grid.sync();
     }
 }
 
@@ -522,6 +566,41 @@ static float *blur_all(Engine *e, const Lattice &L, float *buf, float *tmp, floa
     return src;
 }
 
+// where blur_all leaves its result after d+1 ping-pong passes
+static inline float *blur_result(const Lattice &L, float *buf, float *tmp) { return ((L.d + 1) & 1) ? tmp : buf; }
+
+// co-resident grid limit of the cooperative kernel (0 = cooperative launch unavailable)
+template <int MP>
+static int fused_blur_grid(Engine *e) {
+    static int cached = -1;
+    if (cached < 0) {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mf_blur_fused<MP>, kThreads, 0) != cudaSuccess)
+            per_sm = 0;
+        cached = per_sm * e->sm_count;
+        // opt-in: measured on B200 it shortens the blur kernels themselves (batch 1 @ 375x500: 0.69 -> 0.39 ms
+        // per image) but not the call (1.52 -> 1.49 ms, the host side becomes the limit), changes nothing at
+        // batch 64 @ 321^2 and costs 5 % at batch 64 @ 41^2 (a cooperative launch cannot overlap its neighbours)
+        const char *ev = getenv("DSRG_B200_FUSED_BLUR");
+        if (!ev || atoi(ev) == 0) cached = 0;
+    }
+    return cached;
+}
+
+template <int MP>
+static int blur_fused(Engine *e, float *spY, float *spZ, float *spX, float *biY, float *biZ, float *biX, int b0,
+                      int nb, int grid, cudaStream_t s) {
+    BlurLat sp{e->sp.nbr, e->sp.nbr_stride, e->sp.rowbase, (float4 *)spY, (float4 *)spZ, (float4 *)spX, e->sp.shared, e->sp.d};
+    BlurLat bi{e->bi.nbr, e->bi.nbr_stride, e->bi.rowbase, (float4 *)biY, (float4 *)biZ, (float4 *)biX, e->bi.shared, e->bi.d};
+    void *args[] = {&sp, &bi, &b0, &nb};
+    cudaError_t err = cudaSuccess;
+    DSRG_LAUNCH(e, T_MF_BLUR_FUSED, s,
+                err = cudaLaunchCooperativeKernel((void *)k_mf_blur_fused<MP>, dim3(grid), dim3(kThreads), args, 0, s));
+    DSRG_CUDA_TRY(err);
+    return DSRG_OK;
+}
+
 template <int MP>
 static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp, float *unary_rw,
                     const dsrg_crf_params &p, cudaStream_t s) {
@@ -566,6 +645,10 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
 #define DSRG_BLUR_GRID 8
 #endif
     const int bgrid = (DSRG_BLUR_GRID * e->sm_count) / nlanes;
+    // one cooperative launch for all axes of both lattices (single-lane only: two cooperative grids cannot
+    // be co-resident)
+    const int fmax = nlanes == 1 ? fused_blur_grid<MP>(e) : 0;
+    const int fgrid = fmax < bgrid ? fmax : bgrid;
     // three value buffers per lattice: X = blurred values being sliced, Y = zeroed splat target,
     // Z = blur scratch (the lanes use disjoint row ranges of the same buffers)
     float *spX = e->spA, *spY = e->spB, *spZ = e->spC;
@@ -596,8 +679,15 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
                 continue;
             }
             // the old X is dead: the first blur pass clears it and it becomes the next splat target
-            sp_res = blur_all<MP>(e, e->sp, spY, spZ, spX, b0, nb, T_MF_BLUR_SP, bgrid, st);
-            bi_res = blur_all<MP>(e, e->bi, biY, biZ, biX, b0, nb, T_MF_BLUR_BI, bgrid, st);
+            if (fgrid > 0) {
+                int rc = blur_fused<MP>(e, spY, spZ, spX, biY, biZ, biX, b0, nb, fgrid, st);
+                if (rc) return rc;
+                sp_res = blur_result(e->sp, spY, spZ);
+                bi_res = blur_result(e->bi, biY, biZ);
+            } else {
+                sp_res = blur_all<MP>(e, e->sp, spY, spZ, spX, b0, nb, T_MF_BLUR_SP, bgrid, st);
+                bi_res = blur_all<MP>(e, e->bi, biY, biZ, biX, b0, nb, T_MF_BLUR_BI, bgrid, st);
+            }
         }
         if (it == T) break;
         float *sp_other = (sp_res == spY) ? spZ : spY, *bi_other = (bi_res == biY) ? biZ : biY;
