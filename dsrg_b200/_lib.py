@@ -92,6 +92,7 @@ SIGNATURES = {
     "dsrg_densecrf_add_pairwise_energy": (_i, [_vp] + [_f] * 9 + [_vp]),
     "dsrg_densecrf_map": (_i, [_vp, _i, _vp]),
     "dsrg_densecrf_inference": (_i, [_vp, _i, _vp]),
+    "dsrg_densecrf_release_engines": (None, []),
 }
 
 _LIB = None

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -682,34 +683,61 @@ int dsrg_engine_copy_norm(dsrg_engine *h, int which, int B, float *norm_out) {
 // ------------------------------------------------------------------------------------------------
 struct dsrg_densecrf {
     int W, H, M;
-    dsrg_engine *engine;
     std::vector<float> unary;          // negated energies == the `unary` of CRF()
     std::vector<unsigned char> image;
     dsrg_crf_params params;
     bool has_unary, has_pairwise;
 };
 
+// The reference builds one DenseCRFWrapper per image (CRF.py:21), so the objects must be cheap: they hold
+// host copies of their inputs only, and borrow a process-wide batch-1 engine per label count -- sized for the
+// largest image seen so far and re-shaped per call -- for the duration of inference()/map().
+static std::mutex g_pool_mu;
+static Engine *g_pool[DSRG_MAX_LABELS + 1] = {nullptr};
+
+static Engine *pool_engine(int H, int W, int M) {   // call with g_pool_mu held
+    Engine *e = g_pool[M];
+    if (e && (H > e->Hcap || W > e->Wcap)) {
+        H = H > e->Hcap ? H : e->Hcap;
+        W = W > e->Wcap ? W : e->Wcap;
+        dsrg_engine_destroy((dsrg_engine *)e);
+        e = g_pool[M] = nullptr;
+    }
+    if (!e) {
+        const int Hc = (H + 63) / 64 * 64, Wc = (W + 63) / 64 * 64;   // head-room for slightly larger images
+        e = g_pool[M] = (Engine *)dsrg_engine_create(0, 1, Hc, Wc, M);
+        if (!e) return nullptr;
+    }
+    return e;
+}
+
+void dsrg_densecrf_release_engines(void) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto &e : g_pool) {
+        if (e) dsrg_engine_destroy((dsrg_engine *)e);
+        e = nullptr;
+    }
+}
+
 dsrg_densecrf *dsrg_densecrf_create(int W, int H, int nlabels) {
-    dsrg_engine *eng = dsrg_engine_create(0, 1, H, W, nlabels);
-    if (!eng) return nullptr;
-    dsrg_densecrf *c = new (std::nothrow) dsrg_densecrf();
-    if (!c) {
-        dsrg_engine_destroy(eng);
+    if (W < 1 || H < 1 || nlabels < 1 || nlabels > DSRG_MAX_LABELS || (long long)H * W > (1ll << 24)) {
+        set_error("bad shape (W=%d H=%d nlabels=%d; nlabels <= %d)", W, H, nlabels, DSRG_MAX_LABELS);
         return nullptr;
     }
+    if (dsrg_device_count() < 1) {
+        set_error("no usable CUDA device: this library has no CPU fallback");
+        return nullptr;
+    }
+    dsrg_densecrf *c = new (std::nothrow) dsrg_densecrf();
+    if (!c) return nullptr;
     c->W = W;
     c->H = H;
     c->M = nlabels;
-    c->engine = eng;
     c->has_unary = c->has_pairwise = false;
     return c;
 }
 
-void dsrg_densecrf_destroy(dsrg_densecrf *c) {
-    if (!c) return;
-    dsrg_engine_destroy(c->engine);
-    delete c;
-}
+void dsrg_densecrf_destroy(dsrg_densecrf *c) { delete c; }
 
 int dsrg_densecrf_npixels(const dsrg_densecrf *c) { return c ? c->W * c->H : 0; }
 int dsrg_densecrf_nlabels(const dsrg_densecrf *c) { return c ? c->M : 0; }
@@ -748,7 +776,8 @@ int dsrg_densecrf_add_pairwise_energy(dsrg_densecrf *c, float w1, float theta_al
     return DSRG_OK;
 }
 
-static int densecrf_run(dsrg_densecrf *c, int n_iters) {
+// runs the mean field on the borrowed engine; the caller holds g_pool_mu until its export + copy are done
+static int densecrf_run(dsrg_densecrf *c, int n_iters, Engine **eng) {
     if (!c) {
         set_error("NULL object");
         return DSRG_E_INVALID;
@@ -757,9 +786,12 @@ static int densecrf_run(dsrg_densecrf *c, int n_iters) {
         set_error("add_pairwise_energy must be called before inference/map");
         return DSRG_E_STATE;
     }
-    Engine *e = (Engine *)c->engine;
-    int rc = ensure_staging(e);
+    Engine *e = pool_engine(c->H, c->W, c->M);
+    if (!e) return DSRG_E_CUDA;
+    *eng = e;
+    int rc = dsrg_engine_set_size((dsrg_engine *)e, c->H, c->W);
     if (rc) return rc;
+    if ((rc = ensure_staging(e))) return rc;
     if (!c->has_unary) c->unary.assign((size_t)c->W * c->H * c->M, 0.0f);  // unary.fill(0), densecrf.cpp:117
     c->params.n_iters = n_iters;
     cudaStream_t s = e->own_stream;
@@ -770,9 +802,14 @@ static int densecrf_run(dsrg_densecrf *c, int n_iters) {
 }
 
 int dsrg_densecrf_inference(dsrg_densecrf *c, int n_iters, float *probs_out) {
-    int rc = densecrf_run(c, n_iters);
+    if (!probs_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    Engine *e = nullptr;
+    int rc = densecrf_run(c, n_iters, &e);
     if (rc) return rc;
-    Engine *e = (Engine *)c->engine;
     cudaStream_t s = e->own_stream;
     if ((rc = meanfield_export(e, 1, e->st_out, DSRG_LAYOUT_NHWC, s))) return rc;
     DSRG_CUDA_TRY(cudaMemcpyAsync(probs_out, e->st_out, c->unary.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -780,9 +817,14 @@ int dsrg_densecrf_inference(dsrg_densecrf *c, int n_iters, float *probs_out) {
 }
 
 int dsrg_densecrf_map(dsrg_densecrf *c, int n_iters, int *labels) {
-    int rc = densecrf_run(c, n_iters);
+    if (!labels) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    Engine *e = nullptr;
+    int rc = densecrf_run(c, n_iters, &e);
     if (rc) return rc;
-    Engine *e = (Engine *)c->engine;
     cudaStream_t s = e->own_stream;
     if ((rc = meanfield_export_map(e, 1, e->st_lmap, s))) return rc;
     DSRG_CUDA_TRY(cudaMemcpyAsync(labels, e->st_lmap, (size_t)c->W * c->H * sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -291,7 +291,8 @@ int dsrg_engine_copy_norm(dsrg_engine *e, int which, int B, float *norm_out_host
 /* ------------------------------------------------------------------------------------------
  * Per-object API with the exact surface of the reference's C++ class DenseCRFWrapper
  * (CRF/include/densecrf_wrapper.h:3-28), which krahenbuhl2013/wrapper.pyx:20-60 binds.
- * Host pointers, borrowed for the duration of the call, like the original.
+ * Host pointers, borrowed for the duration of the call, like the original.  Creating an object is cheap
+ * (the reference makes one per image, CRF.py:21): it allocates nothing on the device.
  * ------------------------------------------------------------------------------------------ */
 typedef struct dsrg_densecrf dsrg_densecrf;
 
@@ -306,6 +307,9 @@ int dsrg_densecrf_add_pairwise_energy(dsrg_densecrf *c, float w1, float theta_al
                                       float theta_gamma_2, const unsigned char *im);  /* :18-30 */
 int dsrg_densecrf_map(dsrg_densecrf *c, int n_iters, int *labels);         /* :39-43 */
 int dsrg_densecrf_inference(dsrg_densecrf *c, int n_iters, float *probs_out); /* :45-50 */
+/* The objects borrow a process-wide engine per label count (created on first use, grown to the largest image
+ * seen, serialised by a mutex); this frees those engines' device memory. */
+void dsrg_densecrf_release_engines(void);
 
 #ifdef __cplusplus
 }

@@ -209,3 +209,33 @@ def test_crf_random_shapes_fuzz(torch_cuda):
         got = eng.crf_host(np.ascontiguousarray(unary, np.float32), np.ascontiguousarray(image), api.crf_params(sf))
         assert np.abs(got - want).max() <= TOL, (case, H, W, M, sf, B)
         eng.close()
+
+
+def test_densecrf_objects_share_one_engine(torch_cuda):
+    """The reference makes one DenseCRF per image (CRF.py:21); ours borrow a pooled engine, so objects of
+    different sizes can be created up front and run in any order without leaking state into each other."""
+    from dsrg_b200 import _lib
+    cases = []
+    for i, (H, W) in enumerate([(24, 40), (40, 24), (70, 90), (24, 40)]):
+        p = synth.make_problem(900 + i, H, W, image="smooth" if i % 2 else "noise")
+        pr = np.transpose(p["probs"], (1, 2, 0)).copy()
+        pr[pr < 1e-5] = 1e-5
+        c = api.DenseCRF(W, H, 21)
+        c.set_unary_energy(-np.log(pr).ravel())
+        c.add_pairwise_energy(10, 80, 80, 13, 13, 13, 3, 3, 3, p["image"].ravel())
+        cases.append((c, p["image"], np.log(pr), H, W))
+    for k in (2, 0, 3, 1, 2):
+        c, im, unary, H, W = cases[k]
+        want = crf_oracle.CRF(im, unary, scale_factor=1.0)
+        got = c.inference(10).reshape(H, W, 21)
+        assert np.abs(got - want).max() <= 1e-4
+        lab = c.map(10).reshape(H, W)
+        bad = lab != want.argmax(2)
+        if bad.any():
+            top2 = np.sort(want, axis=2)[:, :, -2:]
+            assert ((top2[:, :, 1] - top2[:, :, 0])[bad] <= 4e-4).all()
+    with pytest.raises(api.DsrgError):
+        api.DenseCRF(8, 8, 33)
+    _lib.lib().dsrg_densecrf_release_engines()
+    got = cases[0][0].inference(10)            # the pool is re-created on demand
+    assert np.isfinite(got).all()
