@@ -1,17 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/all_tests.log 2>&1; echo "all rc=$?"
-tail -8 gpurun_out/all_tests.log
-for fb in 1 0; do
-  echo "== FUSED_BLUR=$fb"
-  DSRG_B200_FUSED_BLUR=$fb timeout 300 python tools/bench_infer.py --cpu 0 > gpurun_out/infer_fb$fb.json 2> gpurun_out/infer.err; echo "infer rc=$?"
-  python - <<PY
-import json
-d=json.load(open('gpurun_out/infer_fb$fb.json'))
-print(d['value'], d['ms_per_image'], d['kernel_ms_per_image'], d['launches_per_image'], d['kernel_classes_ms_per_image'])
-PY
-  DSRG_B200_FUSED_BLUR=$fb timeout 600 python bench.py > gpurun_out/bench_fb$fb.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-  python tools/bench_summary.py gpurun_out/bench_fb$fb.json 2>/dev/null | head -30
-  DSRG_B200_FUSED_BLUR=$fb timeout 600 python bench.py --workload train41 > gpurun_out/bench41_fb$fb.json 2> gpurun_out/bench.err; echo "bench41 rc=$?"
-  python tools/bench_summary.py gpurun_out/bench41_fb$fb.json 2>/dev/null | head -8
+tail -6 gpurun_out/all_tests.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+LB=$PWD/dsrg_b200/lib/libdsrg_b200_lb.so
+DSRG_B200_LIB=$LB timeout 600 python -m pytest tests/test_gpu_crf.py tests/test_gpu_dropin.py -q -m gpu -x > gpurun_out/lb_tests.log 2>&1; echo "lb tests rc=$?"
+tail -4 gpurun_out/lb_tests.log
+for v in base lb base lb; do
+  if [ $v = lb ]; then export DSRG_B200_LIB=$LB; else unset DSRG_B200_LIB; fi
+  timeout 600 python bench.py > gpurun_out/bench_$v.json 2> gpurun_out/bench.err; echo "bench $v rc=$?"
+  python tools/bench_summary.py gpurun_out/bench_$v.json 2>/dev/null | head -5
 done
+unset DSRG_B200_LIB
