@@ -166,7 +166,10 @@ def _cpu_one(args):
         # refinement() with the image already at map resolution: pylayers.py:310-331 minus the zoom
         probs[probs < crf_oracle.MIN_PROB] = crf_oracle.MIN_PROB
         unary = np.ascontiguousarray(np.transpose(probs, (1, 2, 0)))
-        q = crf_oracle.CRF(image, unary, maxiter=T_ITERS, scale_factor=1.0)
+        # the reference's own CRF sources (oracle/_ref/libdensecrf_ref.so, built once in the dev container and
+        # shipped with the snapshot) when present; the C restatement is bit-identical to it and equally fast
+        crf = crf_oracle.CRF_reference if crf_oracle.ref_crf_available() else crf_oracle.CRF
+        q = crf(image, unary, maxiter=T_ITERS, scale_factor=1.0)
         r = np.transpose(np.array(q, np.float64), (2, 0, 1))
         r[r < crf_oracle.MIN_PROB] = crf_oracle.MIN_PROB
         r = r / np.sum(r, axis=0, keepdims=True)
@@ -177,6 +180,19 @@ def _cpu_one(args):
     if "loss" in what:
         loss_oracle.balanced_seed_loss(probs[None], out[None], np.float32)
     return float(np.sum(out))
+
+
+def cpu_kind(what):
+    """'reference' only when everything timed is the reference's own compiled code (CRF-only workloads with
+    oracle/_ref present); the SRG half is always the loop-for-loop Python port."""
+    from oracle import crf_oracle
+    return "reference" if (what == "crf" and crf_oracle.ref_crf_available()) else "port"
+
+
+def cpu_crf_note():
+    from oracle import crf_oracle
+    return ("CRF = the reference's own CRF/src/*.cpp compiled in place (oracle/_ref)" if crf_oracle.ref_crf_available()
+            else "CRF = oracle/crf_oracle.c (restatement)") + ", SRG = loop-for-loop port of generate_seed_step + CC_labeling_8"
 
 
 def cpu_images_per_second(what, batch, n_images, cores, pool=None):
@@ -222,7 +238,8 @@ def run_reference(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "what": what, "H": H, "W": W, "labels": M, "mean_field_iters": T_ITERS,
                    "images_per_step": n},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": cpu_kind(what), "sample": sample,
+                         "code": cpu_crf_note()},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -382,7 +399,7 @@ def run_b200(args, rank, local_rank, world):
         crf_oracle.build()
         n = 6
         v, dt = cpu_images_per_second(what, batch, n, 1, None)
-        cpu_baseline = {"value": v, "unit": "images/s", "cores": 1, "kind": "port",
+        cpu_baseline = {"value": v, "unit": "images/s", "cores": 1, "kind": cpu_kind(what), "code": cpu_crf_note(),
                         "sample": "%d images of the same %s batch, single thread like the reference's serial CRF loop "
                                   "(pylayers.py:325-326); %.1f s of CPU work" % (n, args.workload, dt)}
     if rank == 0:

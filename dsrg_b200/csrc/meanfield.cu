@@ -572,8 +572,11 @@ static inline float *blur_result(const Lattice &L, float *buf, float *tmp) { ret
 // co-resident grid limit of the cooperative kernel (0 = cooperative launch unavailable)
 template <int MP>
 static int fused_blur_grid(Engine *e) {
-    static int cached = -1;
-    if (cached < 0) {
+    static int cache[64];
+    static bool have[64] = {false};
+    int &cached = cache[e->device & 63];
+    if (!have[e->device & 63]) {
+        have[e->device & 63] = true;
         int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
         if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mf_blur_fused<MP>, kThreads, 0) != cudaSuccess)
@@ -623,12 +626,13 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
     const float alpha_bi = 1.0f / (1 + powf(2, -e->bi.d));
     const float c_sp = p.w2 * alpha_sp, c_bi = p.w1 * alpha_bi;
     const size_t smem = sizeof(TileSmem<MP>);
-    static bool attr_done[3] = {false, false, false};
-    if (!attr_done[0]) {
+    static bool attr_done[64] = {false};   // function attributes are per device
+    const int dv = e->device & 63;
+    if (!attr_done[dv]) {
         DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[0] = true;
+        attr_done[dv] = true;
     }
     // Images are independent, so the batch runs as two half-batches on two streams: while one half
     // is in its (DRAM-latency-bound) blur passes the other is in the (shared-memory-bound) tile

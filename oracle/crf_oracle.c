@@ -5,15 +5,18 @@
  * speedinghzl/DSRG's vendored Kraehenbuehl-2013 code.  Only tests/, bench.py's
  * cpu_baseline / --impl reference leg and __graft_entry__.smoke() may load it.
  *
- * Parity status: the reference ships NO golden vectors for this path and its
- * densecrf.cpp / pairwise.cpp cannot be compiled here (Eigen3 is an absent,
- * un-vendored dependency).  The lattice part of this file IS pinned: it is checked
- * bit-for-bit (offsets, barycentrics, blur neighbours, seq/sse compute) against the
- * reference's own CRF/src/permutohedral.cpp compiled in place (oracle/_ref, see
- * oracle/Makefile) by tests/test_oracle_crf.py.  The glue around it (features, norm,
- * Potts, mean-field loop, softmax) is a restatement -> "parity unpinned" for that glue
- * beyond the self-consistency checks in the tests.  Eigen's vectorised exp() and
- * sum() are replaced by expf() and a sequential sum (<= few ulp, far inside 1e-4).
+ * Parity status: PINNED against the reference's own code.  The reference ships no golden
+ * vectors for this path and real Eigen3 is an absent, un-vendored dependency, but its CRF
+ * sources compile unmodified, in place, against a small Eigen stand-in (oracle/eigen_shim):
+ *   - oracle/_ref/libpermuto_ref.so  = CRF/src/permutohedral.cpp: the lattice part of this
+ *     file is checked bit-for-bit (offsets, barycentrics, ranks, blur neighbours, seq/sse
+ *     compute) against it;
+ *   - oracle/_ref/libdensecrf_ref.so = the whole source list of CRF/setup.py:17-25 behind
+ *     DenseCRFWrapper: inference() and map() of this file are BIT-IDENTICAL to it on every
+ *     test case (tests/test_oracle_golden.py), i.e. features, norm, Potts sign, kernel order,
+ *     mean-field loop and softmax structure are the reference's.
+ * What stays unpinned is Eigen's own numerics: its vectorised exp() and packet-wise sum()
+ * are expf() and a sequential sum both here and in the stand-in (<= few ulp, far inside 1e-4).
  *
  * Build flags matter: -O2 -ffp-contract=off and NO -march (the reference build,
  * CRF/setup.py:14-33, passes no arch flags => SSE2 float math, no FMA, MXCSR

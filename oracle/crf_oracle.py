@@ -4,6 +4,8 @@ ctypes bindings for the CPU checkers built by oracle/Makefile:
 
 * ``liboracle_crf.so``  -- the plain-C restatement in oracle/crf_oracle.c
 * ``_ref/libpermuto_ref.so`` -- the reference's own CRF/src/permutohedral.cpp (when built)
+* ``_ref/libdensecrf_ref.so`` -- the reference's own CRF sources behind DenseCRFWrapper (when built):
+  ``RefDenseCRF`` / ``CRF_reference``; the restatement is bit-identical to it (tests/test_oracle_golden.py)
 
 and a Python restatement of the two reference call sites of the CRF:
 ``CRF()`` (CRF/krahenbuhl2013/CRF.py:4-37) and ``DSRGLayer.refinement`` /
@@ -34,8 +36,8 @@ def build(force=False):
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "liboracle_crf.so"], stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/CRF/src/permutohedral.cpp"):
-        ref = os.path.join(_HERE, "_ref", "libpermuto_ref.so")
-        if force or not os.path.exists(ref):
+        refs = [os.path.join(_HERE, "_ref", n) for n in ("libpermuto_ref.so", "libdensecrf_ref.so")]
+        if force or not all(os.path.exists(r) for r in refs):
             subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -214,6 +216,75 @@ class DenseCRF(object):
         if getattr(self, "h", None):
             self._L.oracle_crf_destroy(self.h)
             self.h = None
+
+
+_REFCRF = None
+
+
+def ref_crf_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libdensecrf_ref.so"))
+
+
+def _ref_crf():
+    global _REFCRF
+    if _REFCRF is None:
+        R = C.CDLL(os.path.join(_HERE, "_ref", "libdensecrf_ref.so"))
+        R.ref_densecrf_create.restype = C.c_void_p
+        R.ref_densecrf_create.argtypes = [C.c_int] * 3
+        R.ref_densecrf_destroy.argtypes = [C.c_void_p]
+        R.ref_densecrf_set_unary_energy.argtypes = [C.c_void_p, _f32p]
+        R.ref_densecrf_add_pairwise_energy.argtypes = [C.c_void_p] + [C.c_float] * 9 + [_u8p]
+        R.ref_densecrf_inference.argtypes = [C.c_void_p, C.c_int, _f32p]
+        R.ref_densecrf_map.argtypes = [C.c_void_p, C.c_int, _i32p]
+        _REFCRF = R
+    return _REFCRF
+
+
+class RefDenseCRF(object):
+    """The reference's OWN DenseCRFWrapper (CRF/src/*.cpp compiled in place into oracle/_ref/libdensecrf_ref.so
+    against the Eigen stand-in); same surface as wrapper.pyx:20-60.  Present wherever oracle/_ref was built."""
+
+    def __init__(self, W, H, nlabels):
+        self._R = _ref_crf()
+        self.W, self.H, self.M = int(W), int(H), int(nlabels)
+        self.h = self._R.ref_densecrf_create(self.W, self.H, self.M)
+
+    def set_unary_energy(self, unary_costs):
+        u = np.ascontiguousarray(unary_costs, np.float32)
+        assert u.size == self.W * self.H * self.M
+        self._R.ref_densecrf_set_unary_energy(self.h, u)
+
+    def add_pairwise_energy(self, w1, ta1, ta2, tb1, tb2, tb3, w2, tg1, tg2, im):
+        im = np.ascontiguousarray(im, np.uint8)
+        assert im.size == self.W * self.H * 3
+        self._R.ref_densecrf_add_pairwise_energy(self.h, w1, ta1, ta2, tb1, tb2, tb3, w2, tg1, tg2, im)
+
+    def inference(self, n_iters=10):
+        out = np.empty(self.W * self.H * self.M, np.float32)
+        self._R.ref_densecrf_inference(self.h, int(n_iters), out)
+        return out
+
+    def map(self, n_iters=10):
+        out = np.empty(self.W * self.H, np.int32)
+        self._R.ref_densecrf_map(self.h, int(n_iters), out)
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self._R.ref_densecrf_destroy(self.h)
+            self.h = None
+
+
+def CRF_reference(image, unary, maxiter=10, scale_factor=1.0, color_factor=13):
+    """CRF/krahenbuhl2013/CRF.py:4-37 on top of the reference's own compiled DenseCRFWrapper."""
+    assert image.shape[:2] == unary.shape[:2]
+    H, W = image.shape[:2]
+    nlabels = unary.shape[2]
+    crf = RefDenseCRF(W, H, nlabels)
+    crf.set_unary_energy(-unary.ravel().astype("float32"))
+    crf.add_pairwise_energy(10, 80 / scale_factor, 80 / scale_factor, color_factor, color_factor, color_factor,
+                            3, 3 / scale_factor, 3 / scale_factor, image.ravel().astype("ubyte"))
+    return crf.inference(maxiter).reshape((H, W, nlabels))
 
 
 def CRF(image, unary, maxiter=10, scale_factor=1.0, color_factor=13):

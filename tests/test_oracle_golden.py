@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from conftest import load_golden
+from dsrg_b200 import synth
 from helpers import crf_case_inputs, digest, make_golden, srg_case_inputs
 from oracle import crf_oracle, loss_oracle, srg_oracle
 
@@ -151,3 +152,42 @@ def test_post_oracle_matches_frozen_golden(case):
     # smooth=False is plain numpy: arg-max of the clamped soft-max
     lab0, p0 = post_oracle.predict_mask_ms(im, blobs, smooth=False)
     assert np.array_equal(lab0, p0.argmax(2)) and p0.min() >= np.float32(1e-5)
+
+
+needs_ref_crf = pytest.mark.skipif(not crf_oracle.ref_crf_available(),
+                                   reason="oracle/_ref/libdensecrf_ref.so not built (needs /root/reference once)")
+
+
+@needs_ref_crf
+@pytest.mark.parametrize("name", [c[0] for c in make_golden.CRF_CASES])
+def test_crf_oracle_is_bit_exact_vs_the_reference_build(name):
+    """The C restatement against the reference's OWN CRF sources (densecrf.cpp, pairwise.cpp, ... compiled
+    unmodified, oracle/Makefile) through DenseCRFWrapper: marginals and MAP labels, several iteration counts."""
+    im, unary, sf = crf_case_inputs(name)
+    H, W, M = unary.shape
+    assert np.array_equal(crf_oracle.CRF(im, unary, 10, sf), crf_oracle.CRF_reference(im, unary, 10, sf))
+    o, r = crf_oracle.DenseCRF(W, H, M), crf_oracle.RefDenseCRF(W, H, M)
+    for c in (o, r):
+        c.set_unary_energy(-unary.ravel())
+        c.add_pairwise_energy(10, 80 / sf, 80 / sf, 13, 13, 13, 3, 3 / sf, 3 / sf, im.ravel())
+    for it in (0, 1, 4):
+        assert np.array_equal(o.inference(it), r.inference(it))
+        assert np.array_equal(o.map(it), r.map(it))
+
+
+@needs_ref_crf
+@pytest.mark.parametrize("H,W,M,sf,img", [(97, 131, 21, 1.0, "smooth"), (60, 45, 5, 12.0, "noise"), (33, 33, 2, 1.0, "noise"),
+                                          (161, 161, 21, 1.0, "smooth")])
+def test_crf_oracle_vs_reference_build_other_shapes(H, W, M, sf, img):
+    """incl. M = 2, where Permutohedral::compute takes the seqCompute branch (permutohedral.cpp:600-601)."""
+    rng = np.random.RandomState(H * 7 + M)
+    im = synth.make_image(rng, H, W, img)
+    logits = rng.randn(H, W, M) * 2
+    logits[H // 4: H // 2, W // 3:, 0] += 4
+    e = np.exp(logits - logits.max(2, keepdims=True))
+    pr = (e / e.sum(2, keepdims=True)).astype(np.float32)
+    pr[pr < 1e-5] = 1e-5
+    for unary in (np.log(pr), pr):
+        a = crf_oracle.CRF(im, unary, 10, sf, color_factor=13)
+        b = crf_oracle.CRF_reference(im, unary, 10, sf, color_factor=13)
+        assert np.array_equal(a, b)

@@ -1,14 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/all_tests.log 2>&1; echo "all rc=$?"
-tail -6 gpurun_out/all_tests.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-LB=$PWD/dsrg_b200/lib/libdsrg_b200_lb.so
-DSRG_B200_LIB=$LB timeout 600 python -m pytest tests/test_gpu_crf.py tests/test_gpu_dropin.py -q -m gpu -x > gpurun_out/lb_tests.log 2>&1; echo "lb tests rc=$?"
-tail -4 gpurun_out/lb_tests.log
-for v in base lb base lb; do
-  if [ $v = lb ]; then export DSRG_B200_LIB=$LB; else unset DSRG_B200_LIB; fi
-  timeout 600 python bench.py > gpurun_out/bench_$v.json 2> gpurun_out/bench.err; echo "bench $v rc=$?"
-  python tools/bench_summary.py gpurun_out/bench_$v.json 2>/dev/null | head -5
-done
-unset DSRG_B200_LIB
+timeout 600 python tools/sweep_schedule.py "8,24,32" "8,12,20,24" "8,12,16,28" "6,10,16,32" "8,10,14,32" "4,8,12,16,24" "8,12,18,26" "8,16,40" "10,14,40" "8,12,44" "6,10,14,34" "8,12,20,12,12" 2>&1 | tee gpurun_out/sweep.log
+DSRG_B200_DEBUG_TIMING=1 DSRG_B200_HOST_SCHEDULE="8,12,20,24" timeout 300 python tools/sweep_schedule.py "8,12,20,24" 2>&1 | grep "host pass" | tail -3
+DSRG_B200_DEBUG_TIMING=1 timeout 300 python tools/sweep_schedule.py "8,24,32" 2>&1 | grep "host pass" | tail -3
