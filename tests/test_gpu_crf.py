@@ -239,3 +239,29 @@ def test_densecrf_objects_share_one_engine(torch_cuda):
     _lib.lib().dsrg_densecrf_release_engines()
     got = cases[0][0].inference(10)            # the pool is re-created on demand
     assert np.isfinite(got).all()
+
+
+@pytest.mark.skipif(not crf_oracle.ref_crf_available(), reason="oracle/_ref/libdensecrf_ref.so was not shipped")
+@pytest.mark.parametrize("H,W,sf,img", [(41, 41, 12.0, "smooth"), (97, 131, 1.0, "smooth"), (64, 64, 1.0, "noise")])
+def test_crf_against_the_reference_build_directly(torch_cuda, H, W, sf, img):
+    """CUDA path vs the reference's OWN CRF sources (compiled unmodified into oracle/_ref, oracle/Makefile):
+    marginals within 1e-4, MAP labels equal except at near-ties."""
+    p = synth.make_problem(950 + H, H, W, image=img)
+    pr = np.transpose(p["probs"], (1, 2, 0)).copy()
+    pr[pr < 1e-5] = 1e-5
+    unary = pr if sf > 1 else np.log(pr)
+    want = crf_oracle.CRF_reference(p["image"], unary, 10, sf)
+    eng = api.Engine(1, H, W, 21)
+    got = eng.crf_host(unary[None], p["image"][None], api.crf_params(sf))[0]
+    assert np.abs(got - want).max() <= 1e-4
+    ref = crf_oracle.RefDenseCRF(W, H, 21)
+    ours = api.DenseCRF(W, H, 21)
+    for c in (ref, ours):
+        c.set_unary_energy(-unary.ravel())
+        c.add_pairwise_energy(10, 80 / sf, 80 / sf, 13, 13, 13, 3, 3 / sf, 3 / sf, p["image"].ravel())
+    a, b = ours.map(10), ref.map(10)
+    bad = a != b
+    if bad.any():
+        top2 = np.sort(want.reshape(-1, 21), axis=1)[:, -2:]
+        assert ((top2[:, 1] - top2[:, 0])[bad] <= 4e-4).all()
+    eng.close()
