@@ -465,7 +465,7 @@ void oracle_crf_add_pairwise_energy(OCRF *c, float w1, float ta1, float ta2, flo
                                     float tb3, float w2, float tg1, float tg2,
                                     const unsigned char *im) {
     int W = c->W, H = c->H, N = c->N;
-    float *f2 = (float *)malloc(sizeof(float) * 2 * (size_t)N);
+    float *f2 = (float *)calloc(2 * (size_t)N, sizeof(float));
     for (int j = 0; j < H; j++)
         for (int i = 0; i < W; i++) {
             f2[(size_t)(j * W + i) * 2 + 0] = i / tg1;
@@ -473,7 +473,7 @@ void oracle_crf_add_pairwise_energy(OCRF *c, float w1, float ta1, float ta2, flo
         }
     pairwise_init(&c->pw[0], f2, 2, N, w2);
     free(f2);
-    float *f5 = (float *)malloc(sizeof(float) * 5 * (size_t)N);
+    float *f5 = (float *)calloc(5 * (size_t)N, sizeof(float));
     for (int j = 0; j < H; j++)
         for (int i = 0; i < W; i++) {
             size_t p = (size_t)(j * W + i);
