@@ -142,8 +142,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 template <int MP>
 struct TileSmem {
     static constexpr int CH = MP / 4;
+    static constexpr int CHP = CH + DSRG_ROW_PAD;
     static constexpr int kRows = kMaxLocSp + kMaxLocBi;
-    static constexpr int kBufF4 = (kRows * CH > 256 * CH) ? kRows * CH : 256 * CH;  // staged rows / Q alias
+    static constexpr int kBufF4 = (kRows * CHP > 256 * CHP) ? kRows * CHP : 256 * CHP;  // staged rows / Q alias
     static constexpr int kEntSp = 256 * 3 + 2, kEntBi = 256 * 6 + 2;
     float4 buf[kBufF4];
     int2 ent[kEntSp + kEntBi];  // CSR entries (byte offset of the pixel's Q row, weight bits)
@@ -155,10 +156,10 @@ struct TileSmem {
 template <int MP, int DP1>
 __device__ __forceinline__ void tile_slice_smem(const float4 *vs, const uint16_t *loc, size_t stride,
                                                 const float *w, float coef, float *t) {
-    constexpr int CH = MP / 4;
+    constexpr int CH = MP / 4, CHP = TileSmem<MP>::CHP;
 #pragma unroll
     for (int r = 0; r < DP1; r++) {
-        const float4 *row = vs + (int)__ldg(loc + r * stride) * CH;
+        const float4 *row = vs + (int)__ldg(loc + r * stride) * CHP;
         const float wr = coef * w[r];
 #pragma unroll
         for (int c = 0; c < CH; c++) {
@@ -263,7 +264,8 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     const bool fb_sp = nl_sp < 0, fb_bi = nl_bi < 0;
     const int n_sp = fb_sp ? 0 : nl_sp, n_bi = fb_bi ? 0 : nl_bi;
     const int base_sp = sp.rowbase[b], base_bi = bi.rowbase[b];
-    float4 *vs_sp = sm.buf, *vs_bi = sm.buf + kMaxLocSp * CH;
+    constexpr int CHP = SM::CHP;
+    float4 *vs_sp = sm.buf, *vs_bi = sm.buf + kMaxLocSp * CHP;
     int2 *hdr_sp = sm.hdr, *hdr_bi = sm.hdr + kMaxLocSp;
     int2 *ent_sp = sm.ent, *ent_bi = sm.ent + SM::kEntSp;
     const size_t strideN = (size_t)N;
@@ -285,7 +287,7 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
         (is_sp ? hdr_sp : hdr_bi)[lv] = make_int2(h.x, row);
         if (MODE != MODE_FIRST) {
             mbar_arrive_expect_tx(&sm.bar, kRowBytes);
-            bulk_g2s((is_sp ? vs_sp : vs_bi) + lv * CH, (is_sp ? sp.val_in : bi.val_in) + (size_t)row * MP,
+            bulk_g2s((is_sp ? vs_sp : vs_bi) + lv * CHP, (is_sp ? sp.val_in : bi.val_in) + (size_t)row * MP,
                      kRowBytes, &sm.bar);
         }
         if (MODE != MODE_LAST && lv == (is_sp ? n_sp : n_bi) - 1) {  // the last segment tells the block's length
@@ -371,7 +373,7 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     __syncthreads();  // every thread is done reading the staged rows: reuse the buffer for Q
     float4 *qs = sm.buf;
 #pragma unroll
-    for (int c = 0; c < CH; c++) qs[tid * CH + c] = make_float4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+    for (int c = 0; c < CH; c++) qs[tid * CHP + c] = make_float4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
     __syncthreads();
     // ---- splat ----
     float4 *vout_sp = reinterpret_cast<float4 *>(sp.val_out), *vout_bi = reinterpret_cast<float4 *>(bi.val_out);

@@ -121,7 +121,7 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
             const int nv = perm[lv[r]];
             tl_loc[((size_t)b * DP1 + r) * N + pix] = (uint16_t)nv;
             const int pos = ptr[nv] + atomicAdd(&cnt[nv], 1);
-            pack[pos] = make_int2(tid * (MP * 4), __float_as_int(w[r]));
+            pack[pos] = make_int2(tid * ((MP + 4 * DSRG_ROW_PAD) * 4), __float_as_int(w[r]));  // byte offset of the pixel's (padded) Q row
         }
     }
     if (tid < nloc) {
