@@ -153,16 +153,29 @@ struct TileSmem {
 };
 
 // slice one lattice from the staged rows (shared memory): t += coef * sum_r wn_r * row_r
+// tail1: M = MP - 3 (e.g. 21 labels in 24 lanes): the last chunk holds ONE real channel, so a 32-bit load
+// (one shared-memory wavefront per warp) replaces the 128-bit one (four)
 template <int MP, int DP1>
 __device__ __forceinline__ void tile_slice_smem(const float4 *vs, const uint16_t *loc, size_t stride,
-                                                const float *w, float coef, float *t) {
+                                                const float *w, float coef, float *t, bool tail1) {
     constexpr int CH = MP / 4, CHP = TileSmem<MP>::CHP;
 #pragma unroll
     for (int r = 0; r < DP1; r++) {
         const float4 *row = vs + (int)__ldg(loc + r * stride) * CHP;
         const float wr = coef * w[r];
 #pragma unroll
-        for (int c = 0; c < CH; c++) {
+        for (int c = 0; c < CH - 1; c++) {
+            const float4 v = row[c];
+            t[4 * c + 0] = fmaf(wr, v.x, t[4 * c + 0]);
+            t[4 * c + 1] = fmaf(wr, v.y, t[4 * c + 1]);
+            t[4 * c + 2] = fmaf(wr, v.z, t[4 * c + 2]);
+            t[4 * c + 3] = fmaf(wr, v.w, t[4 * c + 3]);
+        }
+        constexpr int c = CH - 1;
+        if (tail1) {
+            const float v = reinterpret_cast<const float *>(row + c)[0];
+            t[4 * c + 0] = fmaf(wr, v, t[4 * c + 0]);
+        } else {
             const float4 v = row[c];
             t[4 * c + 0] = fmaf(wr, v.x, t[4 * c + 0]);
             t[4 * c + 1] = fmaf(wr, v.y, t[4 * c + 1]);
@@ -333,14 +346,19 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     mbar_wait(&sm.bar, 0);
 
     // ---- slice + update ----
+#ifdef DSRG_NO_TAIL1
+    const bool tail1 = false;
+#else
+    const bool tail1 = (M == MP - 3);
+#endif
     if (MODE != MODE_FIRST && in) {
         if (!fb_sp)
-            tile_slice_smem<MP, 3>(vs_sp, sp.tl_loc + px_sp, strideN, w_sp, c_sp, t);
+            tile_slice_smem<MP, 3>(vs_sp, sp.tl_loc + px_sp, strideN, w_sp, c_sp, t, tail1);
         else
             tile_slice_global<MP, 3>(reinterpret_cast<const float4 *>(sp.val_in), sp.off + px_sp, strideN,
                                      base_sp, w_sp, c_sp, t);
         if (!fb_bi)
-            tile_slice_smem<MP, 6>(vs_bi, bi.tl_loc + px_bi, strideN, w_bi, c_bi, t);
+            tile_slice_smem<MP, 6>(vs_bi, bi.tl_loc + px_bi, strideN, w_bi, c_bi, t, tail1);
         else
             tile_slice_global<MP, 6>(reinterpret_cast<const float4 *>(bi.val_in), bi.off + px_bi, strideN,
                                      base_bi, w_bi, c_bi, t);
