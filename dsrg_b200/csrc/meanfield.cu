@@ -145,10 +145,9 @@ struct TileSmem {
     static constexpr int CHP = CH + DSRG_ROW_PAD;
     static constexpr int kRows = kMaxLocSp + kMaxLocBi;
     static constexpr int kBufF4 = (kRows * CHP > 256 * CHP) ? kRows * CHP : 256 * CHP;  // staged rows / Q alias
-    static constexpr int kEntSp = 256 * 3 + 2, kEntBi = 256 * 6 + 2;
+    static constexpr int kEntSp = 256 * 3 + kMaxLocSp, kEntBi = 256 * 6 + kMaxLocBi;  // segments padded to even
     float4 buf[kBufF4];
     int2 ent[kEntSp + kEntBi];  // CSR entries (byte offset of the pixel's Q row, weight bits)
-    int2 hdr[kRows];            // per local vertex (first entry | quads << 16, global row)
     uint64_t bar;
 };
 
@@ -210,35 +209,50 @@ __device__ __forceinline__ void tile_slice_global(const float4 *vin, const int32
 // lanes of a warp run similar trip counts, and no cross-lane reduction is needed.
 template <int MP>
 __device__ __forceinline__ void tile_splat_csr(float4 *vout_sp, float4 *vout_bi, int n_sp, int n_bi,
-                                               const int2 *hdr_sp, const int2 *hdr_bi, const int2 *ent_sp,
-                                               const int2 *ent_bi, const unsigned char *qs_bytes) {
+                                               const int2 *hdr_sp, const int2 *hdr_bi, int base_sp, int base_bi,
+                                               const int2 *ent_sp, const int2 *ent_bi,
+                                               const unsigned char *qs_bytes) {
     constexpr int CH = MP / 4;
     // 8 lanes per vertex (CH of them active): every quarter-warp of an LDS.128 then reads ONE pixel
     // row (contiguous 96 B), which is bank-conflict free; measured 3 % faster than packing CH lanes
     constexpr int LPV = 8;
+    constexpr int kPairUnroll = kSplatUnroll / 2 > 0 ? kSplatUnroll / 2 : 1;
     static_assert(CH <= LPV, "lane mapping");
     const int pairs_sp = n_sp * LPV, pairs = (n_sp + n_bi) * LPV;
+    const int cq = threadIdx.x & (LPV - 1);  // 256 % LPV == 0: a thread keeps its label quad
+    if (cq >= CH) return;
+    // the headers live in global memory (L1/L2-resident): the next task's header is fetched while the
+    // current segment is walked
+    auto hdr_of = [&](int p) {
+        const bool s = p < pairs_sp;
+        return __ldg((s ? hdr_sp : hdr_bi) + (s ? p : p - pairs_sp) / LPV);
+    };
+    int2 hn = threadIdx.x < pairs ? hdr_of(threadIdx.x) : make_int2(0, 0);
     for (int p = threadIdx.x; p < pairs; p += 256) {
         const bool is_sp = p < pairs_sp;
-        const int q = is_sp ? p : p - pairs_sp;
-        const int lv = q / LPV, cq = q - lv * LPV;
-        if (cq >= CH) continue;
-        const int2 h = (is_sp ? hdr_sp : hdr_bi)[lv];
-        const int2 *ep = (is_sp ? ent_sp : ent_bi) + (h.x & 0xffff);
-        const int n = h.x >> 16;
+        const int2 h = hn;  // (first entry | count << 16, local row id)
+        if (p + 256 < pairs) hn = hdr_of(p + 256);
+        // segments start on even entries and are padded to an even count (weight-0 entry): two per load
+        const int4 *ep = reinterpret_cast<const int4 *>((is_sp ? ent_sp : ent_bi) + (h.x & 0xffff));
+        const int n2 = ((h.x >> 16) + 1) >> 1;
         const unsigned char *qbase = qs_bytes + cq * 16;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll kSplatUnroll
-        for (int it = 0; it < n; ++it) {
-            const int2 en = ep[it];
-            const float w = __int_as_float(en.y);
-            const float4 qv = *reinterpret_cast<const float4 *>(qbase + en.x);
-            a.x = fmaf(w, qv.x, a.x);
-            a.y = fmaf(w, qv.y, a.y);
-            a.z = fmaf(w, qv.z, a.z);
-            a.w = fmaf(w, qv.w, a.w);
+#pragma unroll kPairUnroll
+        for (int it = 0; it < n2; ++it) {
+            const int4 en = ep[it];
+            const float w0 = __int_as_float(en.y), w1 = __int_as_float(en.w);
+            const float4 q0 = *reinterpret_cast<const float4 *>(qbase + en.x);
+            const float4 q1 = *reinterpret_cast<const float4 *>(qbase + en.z);
+            a.x = fmaf(w0, q0.x, a.x);
+            a.y = fmaf(w0, q0.y, a.y);
+            a.z = fmaf(w0, q0.z, a.z);
+            a.w = fmaf(w0, q0.w, a.w);
+            a.x = fmaf(w1, q1.x, a.x);
+            a.y = fmaf(w1, q1.y, a.y);
+            a.z = fmaf(w1, q1.z, a.z);
+            a.w = fmaf(w1, q1.w, a.w);
         }
-        atomicAdd((is_sp ? vout_sp : vout_bi) + (size_t)h.y * CH + cq, a);
+        atomicAdd((is_sp ? vout_sp : vout_bi) + (size_t)((is_sp ? base_sp : base_bi) + h.y) * CH + cq, a);
     }
 }
 
@@ -279,7 +293,7 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     const int base_sp = sp.rowbase[b], base_bi = bi.rowbase[b];
     constexpr int CHP = SM::CHP;
     float4 *vs_sp = sm.buf, *vs_bi = sm.buf + kMaxLocSp * CHP;
-    int2 *hdr_sp = sm.hdr, *hdr_bi = sm.hdr + kMaxLocSp;
+    const int2 *hdr_sp = sp.tl_hdr + ti_sp * kMaxLocSp, *hdr_bi = bi.tl_hdr + ti_bi * kMaxLocBi;  // global, L1/L2-resident
     int2 *ent_sp = sm.ent, *ent_bi = sm.ent + SM::kEntSp;
     const size_t strideN = (size_t)N;
     const size_t px_sp = (size_t)sb_sp * 3 * N + pix, px_bi = (size_t)sb_bi * 6 * N + pix;
@@ -295,16 +309,15 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     for (int i = tid; i < n_sp + n_bi; i += 256) {  // up to 128 + 256 local vertices
         const bool is_sp = i < n_sp;
         const int lv = is_sp ? i : i - n_sp;
-        const int2 h = is_sp ? sp.tl_hdr[ti_sp * kMaxLocSp + lv] : bi.tl_hdr[ti_bi * kMaxLocBi + lv];
+        const int2 h = __ldg((is_sp ? hdr_sp : hdr_bi) + lv);
         const int row = (is_sp ? base_sp : base_bi) + h.y;
-        (is_sp ? hdr_sp : hdr_bi)[lv] = make_int2(h.x, row);
         if (MODE != MODE_FIRST) {
             mbar_arrive_expect_tx(&sm.bar, kRowBytes);
             bulk_g2s((is_sp ? vs_sp : vs_bi) + lv * CHP, (is_sp ? sp.val_in : bi.val_in) + (size_t)row * MP,
                      kRowBytes, &sm.bar);
         }
         if (MODE != MODE_LAST && lv == (is_sp ? n_sp : n_bi) - 1) {  // the last segment tells the block's length
-            const uint32_t bytes = (uint32_t)(((h.x & 0xffff) + (h.x >> 16) + 1) & ~1) * 8u;
+            const uint32_t bytes = (uint32_t)((h.x & 0xffff) + (((h.x >> 16) + 1) & ~1)) * 8u;
             mbar_arrive_expect_tx(&sm.bar, bytes);
             bulk_g2s(is_sp ? ent_sp : ent_bi,
                      is_sp ? sp.tl_pack + ti_sp * sp.entcap : bi.tl_pack + ti_bi * bi.entcap, bytes, &sm.bar);
@@ -397,7 +410,7 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     float4 *vout_sp = reinterpret_cast<float4 *>(sp.val_out), *vout_bi = reinterpret_cast<float4 *>(bi.val_out);
     if (fb_sp && in) tile_splat_direct<MP, 3>(vout_sp, sp.off + px_sp, strideN, base_sp, w_sp, t);
     if (fb_bi && in) tile_splat_direct<MP, 6>(vout_bi, bi.off + px_bi, strideN, base_bi, w_bi, t);
-    tile_splat_csr<MP>(vout_sp, vout_bi, n_sp, n_bi, hdr_sp, hdr_bi, ent_sp, ent_bi,
+    tile_splat_csr<MP>(vout_sp, vout_bi, n_sp, n_bi, hdr_sp, hdr_bi, base_sp, base_bi, ent_sp, ent_bi,
                        reinterpret_cast<const unsigned char *>(qs));
 }
 

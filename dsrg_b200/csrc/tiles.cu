@@ -95,9 +95,10 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
         scnt[rank] = mycnt;    // counts in the new order
     }
     __syncthreads();
-    // exclusive scan of the reordered counts -> ptr
+    // exclusive scan of the reordered counts, each rounded up to an even number -> ptr: every segment then
+    // starts on a 16-byte boundary and the consumer reads its entries two at a time (one LDS.128)
     {
-        const int v = tid < nloc ? scnt[tid] : 0;
+        const int v = tid < nloc ? ((scnt[tid] + 1) & ~1) : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -127,12 +128,9 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
     if (tid < nloc) {
         const int nv = perm[tid];
         tl_hdr[((size_t)b * ntiles + tile) * MAXLOC + nv] = make_int2(ptr[nv] | (mycnt << 16), rows_s[tid]);
+        if (mycnt & 1) pack[ptr[nv] + mycnt] = make_int2(0, 0);  // padding entry: pixel 0 with weight 0
     }
-    if (tid == 0) {
-        const int total = ptr[nloc - 1] + scnt[nloc - 1];
-        if (total & 1) pack[total] = make_int2(0, 0);  // the block is bulk-copied in 16-byte units
-        tl_nloc[tile] = nloc;
-    }
+    if (tid == 0) tl_nloc[tile] = nloc;
 }
 
 int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s) {
