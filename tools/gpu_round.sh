@@ -1,10 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-L=$PWD/dsrg_b200/lib
-timeout 900 python -m pytest tests/test_gpu_crf.py -q -m gpu -x > gpurun_out/all_tests.log 2>&1; echo "tests rc=$?"
-tail -3 gpurun_out/all_tests.log
-for v in prev base prev base; do
-  if [ $v = base ]; then unset DSRG_B200_LIB; else export DSRG_B200_LIB=$L/libdsrg_b200_$v.so; fi
-  timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_$v.json 2> gpurun_out/bench.err; echo "bench $v rc=$?"
-  python tools/bench_summary.py gpurun_out/bench_$v.json 2>/dev/null | head -3
-done
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_mf_tile" -s 12 -c 2 -o gpurun_out/prof_r1z_tile python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_t.log 2>&1
+timeout 300 ncu --set full --clock-control none -k regex:"k_lattice_insert<5>|k_tile_build<6|k_srg_label|k_srg_merge|k_srg_emit|k_norm_splat" -s 6 -c 6 -o gpurun_out/prof_r1z_misc python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_m.log 2>&1
+ls -la gpurun_out/*.ncu-rep
