@@ -283,6 +283,16 @@ static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, c
     std::vector<char> packed(nchunks, 0);
     int next_unpack = 0;
     static const bool dbg = getenv("DSRG_B200_DEBUG_TIMING") != nullptr;
+    // debug timeline (DSRG_B200_DEBUG_TIMING): per chunk H2D begin/end, kernels begin/end, D2H end
+    std::vector<cudaEvent_t> tl;
+    auto mark = [&](cudaStream_t st) {
+        if (!dbg) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        tl.push_back(ev);
+    };
+    mark(s_in);  // time origin
     double t_pack = 0, t_unpack = 0, t_issue = 0, t_wait = 0, t0 = omp_get_wtime();
     auto finish_chunk = [&](int c) {  // host side of a finished chunk
         const int b0 = cb0[c], nb = cnb[c];
@@ -297,6 +307,7 @@ static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, c
         const size_t o = (size_t)b0 * img_elems, n = (size_t)nb * img_elems;
         // ---- H2D of what needs no packing starts first, the cues are packed meanwhile
         double ti = omp_get_wtime();
+        mark(s_in);
         DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_labels + (size_t)b0 * e->M, labels + (size_t)b0 * e->M,
                                       (size_t)nb * e->M * sizeof(float), cudaMemcpyHostToDevice, s_in));
         DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary + o, probs + o, n * sizeof(float), cudaMemcpyHostToDevice, s_in));
@@ -317,8 +328,10 @@ static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, c
             DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image + (size_t)b0 * e->N * 3, image + (size_t)b0 * e->N * 3,
                                           (size_t)nb * e->N * 3, cudaMemcpyHostToDevice, s_in));
         DSRG_CUDA_TRY(cudaEventRecord(e->pipe_events[3 * c], s_in));
+        mark(s_in);
         // ---- kernels
         DSRG_CUDA_TRY(cudaStreamWaitEvent(s, e->pipe_events[3 * c], 0));
+        mark(s);
         dim3 gb(cdiv(n_img, kThreads), nb);
         if (ok) {
             DSRG_LAUNCH(e, T_WIRE, s,
@@ -341,6 +354,7 @@ static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, c
             if ((rc = meanfield_export(e, nb, e->st_cues + o, DSRG_LAYOUT_NCHW, s))) return rc;
         }
         DSRG_CUDA_TRY(cudaEventRecord(e->pipe_events[3 * c + 1], s));
+        mark(s);
         // ---- D2H
         DSRG_CUDA_TRY(cudaStreamWaitEvent(s_out, e->pipe_events[3 * c + 1], 0));
         if (ok) {
@@ -361,6 +375,7 @@ static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, c
         if (crf_out)
             DSRG_CUDA_TRY(cudaMemcpyAsync(crf_out + o, e->st_cues + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         DSRG_CUDA_TRY(cudaEventRecord(e->pipe_events[3 * c + 2], s_out));
+        mark(s_out);
         t_issue += omp_get_wtime() - ti;
         // ---- host: finish whatever has already come back while the GPU works on this chunk
         while (next_unpack < c && cudaEventQuery(e->pipe_events[3 * next_unpack + 2]) == cudaSuccess)
@@ -373,6 +388,16 @@ static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, c
         finish_chunk(next_unpack);
     }
     DSRG_CUDA_TRY(cudaStreamSynchronize(s_out));
+    if (dbg && !tl.empty()) {
+        fprintf(stderr, "[dsrg host pass] timeline (ms from the first H2D; chunk: h2d begin-end | kernels begin-end | d2h end):");
+        for (int c = 0; c < nchunks; c++) {
+            float t[5];
+            for (int k = 0; k < 5; k++) cudaEventElapsedTime(&t[k], tl[0], tl[1 + 5 * c + k]);
+            fprintf(stderr, "  [%d img: %.2f-%.2f | %.2f-%.2f | %.2f]", cnb[c], t[0], t[1], t[2], t[3], t[4]);
+        }
+        fprintf(stderr, "\n");
+        for (auto ev : tl) cudaEventDestroy(ev);
+    }
     if (dbg)
         fprintf(stderr, "[dsrg host pass] total %.2f ms: pack %.2f issue %.2f unpack %.2f wait %.2f (threads %d, chunks %d)\n",
                 1e3 * (omp_get_wtime() - t0), 1e3 * t_pack, 1e3 * t_issue, 1e3 * t_unpack, 1e3 * t_wait, host_threads(),
