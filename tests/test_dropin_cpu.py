@@ -81,3 +81,27 @@ def test_softmax_and_constrain_loss_oracles_are_self_consistent():
     for idx in [(0, 1, 2, 2), (1, 3, 0, 1), (0, 0, 0, 0)]:
         assert abs(_num_grad(lambda q: loss_oracle.constrain_loss(q, ls), pr, idx, 1e-6) - gp[idx]) < 1e-6
         assert abs(_num_grad(lambda q: loss_oracle.constrain_loss(pr, q), ls, idx, 1e-6) - gl[idx]) < 1e-6
+
+
+def test_annotation_layer_and_postprocess_surface(tmp_path):
+    """AnnotationLayer keeps the reference's setup / reshape contract (pylayers.py:348-367) without touching the
+    GPU; the post-processing module exposes the two predict_mask() tails."""
+    import pickle
+    assert hasattr(pylayers, "AnnotationLayer")
+    layer = pylayers.AnnotationLayer()
+    layer.param_str = "{}"
+    with pytest.raises(Exception):                       # "The layer needs two inputs!"
+        layer.setup([fake_caffe.Blob()], [fake_caffe.Blob()] * 3)
+    with open(str(tmp_path / "localization_cues.pickle"), "wb") as f:
+        pickle.dump({"0_labels": np.array([3]), "0_cues": np.zeros((3, 0), np.int64)}, f, protocol=2)
+    layer.param_str = "{'root': '%s'}" % str(tmp_path)   # default file name and mirror=False like the reference
+    bottom = [fake_caffe.Blob(np.zeros((2, 1, 1, 1))), fake_caffe.Blob(np.zeros((2, 3, 33, 47)))]
+    top = [fake_caffe.Blob(), fake_caffe.Blob(), fake_caffe.Blob()]
+    layer.setup(bottom, top)
+    assert layer._cue_name == "localization_cues.pickle" and layer.is_mirror is False
+    layer.reshape(bottom, top)
+    assert [t.data.shape for t in top] == [(2, 1, 1, 21), (2, 21, 41, 41), (2, 3, 33, 47)]
+    from dsrg_b200 import postprocess
+    assert list(inspect.signature(postprocess.predict_mask_ms).parameters)[:3] == ["im", "scores_per_scale", "smooth"]
+    assert list(inspect.signature(postprocess.predict_mask_gt).parameters)[:4] == ["im", "scores", "labels", "smooth"]
+    assert postprocess.EPS == 0.00001
