@@ -231,7 +231,7 @@ def run_reference(args, rank, world):
         dt = time.perf_counter() - t
     value = n * args.steps / dt
     sample = "%d images/step (1 per host thread) of the %s workload, %d steps, multiprocessing.Pool(%d)" % (n, args.workload, args.steps, cores)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "images/s, SRG + DenseCRF pass at %dx%dx%d" % (H, W, M), "value": value,
         "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -241,7 +241,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": cpu_kind(what), "sample": sample,
                          "code": cpu_crf_note()},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }))
 
 
 # --------------------------------------------------------------------------------------------
@@ -403,7 +403,7 @@ def run_b200(args, rank, local_rank, world):
                         "sample": "%d images of the same %s batch, single thread like the reference's serial CRF loop "
                                   "(pylayers.py:325-326); %.1f s of CPU work" % (n, args.workload, dt)}
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "images/s, SRG + DenseCRF pass at %dx%dx%d" % (H, W, M), "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -414,10 +414,30 @@ def run_b200(args, rank, local_rank, world):
                        "parallelism": "dp%d (images shard, no data-path collective)" % world},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "kernels": kernels, "cpu_baseline": cpu_baseline,
-        }), flush=True)
+        }))
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Libraries print there too (NCCL's version banner
+    ignores NCCL_DEBUG_FILE at NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr for the rest of the run
+    and the JSON line is written to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
 
 
 def main():
@@ -435,6 +455,7 @@ def main():
     args = ap.parse_args()
     global IMAGE_VARIANT
     IMAGE_VARIANT = args.images
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
