@@ -354,7 +354,7 @@ def run_b200(args, rank, local_rank, world):
 
     # end to end through the host-buffer C-ABI entry point (pinned host memory, copies inside)
     e2e = None
-    if what in ("crf+srg", "crf+srg+loss", "srg", "crf"):
+    if what in ("crf+srg", "crf+srg+loss", "srg", "crf") and not args.no_e2e:
         h_labels = api.pinned_empty(batch["labels"].shape, np.float32); h_labels[...] = batch["labels"]
         h_probs = api.pinned_empty(batch["probs"].shape, np.float32); h_probs[...] = batch["probs"]
         h_cues = api.pinned_empty(batch["cues"].shape, np.float32); h_cues[...] = batch["cues"]
@@ -449,6 +449,7 @@ def main():
     ap.add_argument("--workload", default="dsrg321", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning aid: skip the host-buffer leg (the line is then not a valid result)")
     ap.add_argument("--images", default="smooth", choices=["smooth", "noise"],
                     help="synthetic image variant: smooth (headline) or uniform noise (worst case: every tile "
                          "overflows the shared-memory path)")
