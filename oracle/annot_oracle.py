@@ -2,8 +2,10 @@
 (pylayers/pylayers/pylayers.py:369-387), the data layer that turns image tags and sparse localisation
 cues into the dense blobs the hot path consumes.  Only tests/ may import it.
 
-Parity status: unpinned by the reference (no test ships for the layer); the statements below are the
-reference's own numpy statements, kept in order, including the order of the np.random draws.
+Parity status: pinned against the reference's own AnnotationLayer.forward executed in place
+(oracle/ref_layers.py:annotation_layer_forward -> tests/golden/layers_ref.npz, compared bit for bit in
+tests/test_oracle_golden.py); the statements below follow the reference's numpy statements in order,
+including the order of the np.random draws.
 """
 import numpy as np
 

@@ -3,9 +3,12 @@
 numpy restatement of BalancedSeedLossLayer (pylayers/pylayers/pylayers.py:120-152).  The
 reference builds the forward/backward with Theano 0.8.2 (absent here, un-vendored): forward is
 restated expression by expression (:129-139), backward is the analytic gradient of that
-expression (what ``T.grad`` returns).  Parity unpinned (no Theano to run, no reference test).
-float32 like ``T.ftensor4``; the reduction order inside Theano is unspecified, so tests use a
-relative tolerance (1e-5) against a float64 evaluation of the same formula.
+expression (what ``T.grad`` returns).  Pinned against the reference's OWN layer classes: their class
+bodies are executed in place by oracle/ref_layers.py (Theano itself is absent and replaced by
+oracle/theano_shim.py, torch autograd underneath); tests/golden/layers_ref.npz freezes those outputs
+and tests/test_oracle_golden.py holds these restatements to them at 1e-12 (float64 evaluation) -- also
+for SoftmaxLayer and ConstrainLossLayer below.  What stays unpinned is Theano's own float32 reduction
+order (unspecified), hence the relative tolerance (1e-5) of the GPU tests.
 """
 import numpy as np
 

@@ -8,11 +8,14 @@ Runs ONLY in the dev container (needs /root/reference):
   * lattice: the reference's own CRF/src/permutohedral.cpp (oracle/_ref) on real feature
     matrices -> tests/golden/lattice_ref.npz (vertex counts, exact sums / checksums of
     offsets, barycentrics, ranks, neighbours and of seq/sse compute outputs)
+  * layers: the reference's own SoftmaxLayer / BalancedSeedLossLayer / ConstrainLossLayer / AnnotationLayer
+    class bodies executed in place (oracle/ref_layers.py, Theano stand-in oracle/theano_shim.py), float64
+    and float32 -> tests/golden/layers_ref.npz (pins oracle/loss_oracle.py and oracle/annot_oracle.py)
   * CRF: oracle/crf_oracle.c marginals (restatement; its lattice is pinned by the previous
     item) -> tests/golden/crf_oracle_*.npz, so GPU runs have a frozen target even if the
     oracle sources change later.
 
-usage: python tests/golden/make_golden.py
+usage: python tests/golden/make_golden.py [srg lattice crf post layers]   (default: all)
 """
 import hashlib
 import os
@@ -162,10 +165,62 @@ def make_post():
         print("post", name, lab.shape, np.unique(lab))
 
 
+def layer_inputs(seed=0, N=3, C=21, H=9, W=7):
+    """Small seeded inputs of the loss layers: probs with values at the 1e-4 clamp, seed masks with an image
+    without foreground and one without background seeds, smoothed log-probs on both sides of the clip range."""
+    rng = np.random.RandomState(4242 + seed)
+    logits = (3 * rng.randn(N, C, H, W)).astype(np.float32)
+    p = np.exp(logits - logits.max(1, keepdims=True))
+    p = np.maximum(p / p.sum(1, keepdims=True), 1e-4).astype(np.float32)
+    lab = (rng.rand(N, C, H, W) < 0.1).astype(np.float32)
+    lab[N - 2, 1:] = 0
+    lab[N - 1, 0] = 0
+    top_diff = rng.randn(N, C, H, W).astype(np.float32)
+    log_smooth = np.log(np.maximum(p * rng.uniform(0.01, 30, p.shape), 1e-6)).astype(np.float32)
+    return logits, p, lab, top_diff, log_smooth
+
+
+def annot_inputs(n_images=6, seed=3, h=41, w=41, M=21):
+    rng = np.random.RandomState(seed)
+    d = {}
+    for i in range(n_images):
+        k = rng.randint(1, 4)
+        tags = np.sort(rng.choice(np.arange(1, M), size=k, replace=False))
+        d['%i_labels' % i] = tags
+        cls = np.concatenate([[0], tags])
+        K = 0 if i == 3 else rng.randint(1, 300)
+        d['%i_cues' % i] = np.stack([rng.choice(cls, K), rng.randint(0, h, K), rng.randint(0, w, K)]).astype(np.int64)
+    ids = np.array([5, 0, 3, 1, 2, 2], np.float32)
+    images = (rng.rand(len(ids), 3, 17, 23) * 255 - 110).astype(np.float32)
+    return d, ids, images
+
+
+def make_layers():
+    from oracle import ref_layers
+    rec = {}
+    for seed in (0, 1):
+        logits, p, lab, td, ls = layer_inputs(seed)
+        rec["in%d_sha256" % seed] = digest(logits, p, lab, td, ls)
+        for dt in ("float64", "float32"):
+            k = "s%d_%s_" % (seed, dt)
+            rec[k + "softmax_probs"], rec[k + "softmax_grad"] = ref_layers.softmax_layer(logits, td, dt)
+            rec[k + "seed_loss"], rec[k + "seed_grad"] = ref_layers.balanced_seed_loss_layer(p, lab, dt)
+            rec[k + "constrain_loss"], rec[k + "constrain_g0"], rec[k + "constrain_g1"] = \
+                ref_layers.constrain_loss_layer(p, ls, dt)
+        print("layers seed", seed, float(rec["s%d_float64_seed_loss" % seed]), float(rec["s%d_float64_constrain_loss" % seed]))
+    d, ids, images = annot_inputs()
+    for mirror in (False, True):
+        t0, t1, t2 = ref_layers.annotation_layer_forward(d, ids, images, mirror, seed=11)
+        k = "annot_m%d_" % int(mirror)
+        rec[k + "labels"], rec[k + "cues_bits"], rec[k + "images_sha256"] = t0, np.packbits(t1.astype(np.uint8)), digest(t2)
+        rec[k + "cues_shape"] = np.array(t1.shape)
+        print("annotation mirror", mirror, int(t1.sum()))
+    np.savez_compressed(os.path.join(OUT, "layers_ref.npz"), **rec)
+
+
 if __name__ == "__main__":
     assert srg_oracle.reference_available(), "needs /root/reference"
+    what = sys.argv[1:] or ["srg", "lattice", "crf", "post", "layers"]
     crf_oracle.build(force=True)
-    make_srg()
-    make_lattice()
-    make_crf()
-    make_post()
+    for w in what:
+        {"srg": make_srg, "lattice": make_lattice, "crf": make_crf, "post": make_post, "layers": make_layers}[w]()

@@ -191,3 +191,65 @@ def test_crf_oracle_vs_reference_build_other_shapes(H, W, M, sf, img):
         a = crf_oracle.CRF(im, unary, 10, sf, color_factor=13)
         b = crf_oracle.CRF_reference(im, unary, 10, sf, color_factor=13)
         assert np.array_equal(a, b)
+
+
+# ---- a12 / f1 / f4: the loss and annotation oracles against the reference's own layer classes -------------------
+# tests/golden/layers_ref.npz holds the outputs of the reference's SoftmaxLayer / BalancedSeedLossLayer /
+# ConstrainLossLayer / AnnotationLayer class bodies executed in place (oracle/ref_layers.py; Theano is replaced by
+# oracle/theano_shim.py, float64 and float32 evaluation).
+@pytest.mark.parametrize("seed", [0, 1])
+def test_loss_oracles_match_the_reference_layers_golden(seed):
+    g = load_golden("layers_ref.npz")
+    logits, p, lab, td, ls = make_golden.layer_inputs(seed)
+    assert digest(logits, p, lab, td, ls) == str(g["in%d_sha256" % seed]), "input generator drifted"
+    k = "s%d_float64_" % seed
+    tight = dict(rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(loss_oracle.softmax_layer_forward(logits), g[k + "softmax_probs"], **tight)
+    np.testing.assert_allclose(loss_oracle.softmax_layer_backward(logits, td), g[k + "softmax_grad"], **tight)
+    np.testing.assert_allclose(loss_oracle.balanced_seed_loss(p, lab), g[k + "seed_loss"], **tight)
+    np.testing.assert_allclose(loss_oracle.balanced_seed_loss_grad(p, lab), g[k + "seed_grad"], **tight)
+    np.testing.assert_allclose(loss_oracle.constrain_loss(p, ls), g[k + "constrain_loss"], **tight)
+    w0, w1 = loss_oracle.constrain_loss_grad(p, ls)
+    np.testing.assert_allclose(w0, g[k + "constrain_g0"], **tight)
+    np.testing.assert_allclose(w1, g[k + "constrain_g1"], **tight)
+    # the float32 evaluation (what T.ftensor4 computes in) stays within the tolerance the GPU tests use
+    k32 = "s%d_float32_" % seed
+    for name in ("softmax_probs", "softmax_grad", "seed_loss", "seed_grad", "constrain_loss", "constrain_g0", "constrain_g1"):
+        np.testing.assert_allclose(g[k32 + name], g[k + name], rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("mirror", [False, True])
+def test_annotation_oracle_matches_the_reference_layer_golden(mirror):
+    from oracle import annot_oracle
+    g = load_golden("layers_ref.npz")
+    d, ids, images = make_golden.annot_inputs()
+    np.random.seed(11)
+    t0, t1, t2 = annot_oracle.annotation_forward(d, ids, images, mirror)
+    k = "annot_m%d_" % int(mirror)
+    shape = tuple(g[k + "cues_shape"])
+    want1 = np.unpackbits(g[k + "cues_bits"])[: int(np.prod(shape))].reshape(shape).astype(np.float32)
+    assert np.array_equal(t0, g[k + "labels"]) and np.array_equal(t1, want1) and digest(t2) == str(g[k + "images_sha256"])
+
+
+def _ref_layers():
+    from oracle import ref_layers
+    return ref_layers
+
+
+@pytest.mark.skipif(not srg_oracle.reference_available(), reason="needs /root/reference (dev container)")
+def test_reference_layers_run_in_place_random_sweep():
+    """Live: the reference's own layer classes (through the Theano stand-in) against the restatements on fresh inputs."""
+    rl = _ref_layers()
+    for seed in (5, 6, 7):
+        logits, p, lab, td, ls = make_golden.layer_inputs(seed, N=2 + seed % 3, H=5 + seed, W=11 - seed)
+        loss, grad = rl.balanced_seed_loss_layer(p, lab, "float64")
+        np.testing.assert_allclose(loss, loss_oracle.balanced_seed_loss(p, lab), rtol=1e-12)
+        np.testing.assert_allclose(grad, loss_oracle.balanced_seed_loss_grad(p, lab), rtol=1e-12, atol=1e-15)
+        pr, gd = rl.softmax_layer(logits, td, "float64")
+        np.testing.assert_allclose(pr, loss_oracle.softmax_layer_forward(logits), rtol=1e-12)
+        np.testing.assert_allclose(gd, loss_oracle.softmax_layer_backward(logits, td), rtol=1e-10, atol=1e-15)
+        cl, g0, g1 = rl.constrain_loss_layer(p, ls, "float64")
+        np.testing.assert_allclose(cl, loss_oracle.constrain_loss(p, ls), rtol=1e-12)
+        w0, w1 = loss_oracle.constrain_loss_grad(p, ls)
+        np.testing.assert_allclose(g0, w0, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(g1, w1, rtol=1e-12, atol=1e-15)
