@@ -170,10 +170,7 @@ def _cpu_one(args):
         # shipped with the snapshot) when present; the C restatement is bit-identical to it and equally fast
         crf = crf_oracle.CRF_reference if crf_oracle.ref_crf_available() else crf_oracle.CRF
         q = crf(image, unary, maxiter=T_ITERS, scale_factor=1.0)
-        r = np.transpose(np.array(q, np.float64), (2, 0, 1))
-        r[r < crf_oracle.MIN_PROB] = crf_oracle.MIN_PROB
-        r = r / np.sum(r, axis=0, keepdims=True)
-        out = r
+        out = crf_oracle.renormalise(np.transpose(q, (2, 0, 1)))   # pylayers.py:328-330
     if "srg" in what:
         src = out if out is not None else probs.astype(np.float64)
         out = srg_oracle.srg_faithful(labels, cues, src, TH1, TH2)

@@ -35,6 +35,7 @@ SIGNATURES = {
     "dsrg_version": (_i, []),
     "dsrg_last_error": (C.c_char_p, []),
     "dsrg_device_count": (_i, []),
+    "dsrg_current_device": (_i, []),
     "dsrg_host_alloc": (_vp, [_sz]),
     "dsrg_host_free": (None, [_vp]),
     "dsrg_crf_params_default": (None, [_pp, _f, _f, _i]),

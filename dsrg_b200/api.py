@@ -44,28 +44,46 @@ def _stream(stream):
     return C.c_void_p(int(stream))
 
 
+class _PinnedBlock(object):
+    """Owner of one dsrg_host_alloc block; the numpy arrays built over it keep it alive through the ctypes
+    buffer they wrap (numpy's ``base`` chain), and the block is returned with dsrg_host_free when the last of
+    them is gone."""
+
+    def __init__(self, L, nbytes):
+        self._L = L
+        self.ptr = L.dsrg_host_alloc(nbytes)
+        if not self.ptr:
+            raise DsrgError(_lib.E_NOMEM, L.dsrg_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            try:
+                self._L.dsrg_host_free(self.ptr)
+            except Exception:
+                pass
+            self.ptr = None
+
+
 def pinned_empty(shape, dtype):
-    """numpy array over pinned host memory from dsrg_host_alloc (freed with the array)."""
+    """numpy array over pinned host memory from dsrg_host_alloc (freed when the array and its views are)."""
     L = _lib.lib()
     dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
-    p = L.dsrg_host_alloc(max(n, 16))
-    if not p:
-        raise DsrgError(_lib.E_NOMEM, L.dsrg_last_error().decode())
-    buf = (C.c_char * max(n, 16)).from_address(p)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _PINNED[arr.ctypes.data] = (p, buf)
-    return arr
-
-
-_PINNED = {}
+    n = max(int(np.prod(shape)) * dtype.itemsize, 16)
+    block = _PinnedBlock(L, n)
+    buf = (C.c_char * n).from_address(block.ptr)
+    buf._dsrg_block = block   # the ctypes object is the base of every array below: it carries the owner
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 class Engine(object):
     """dsrg_engine: all device buffers for batches of up to ``max_batch`` H x W x M problems."""
 
-    def __init__(self, max_batch, H, W, M=21, device=0):
+    def __init__(self, max_batch, H, W, M=21, device=None):
+        """device None: the calling thread's current CUDA device (dsrg_current_device: what caffe.set_device /
+        torch.cuda.set_device selected, or DSRG_B200_DEVICE)."""
         self._L = _lib.lib()
+        if device is None:
+            device = self._L.dsrg_current_device()
         self.max_batch, self.H, self.W, self.M, self.device = int(max_batch), int(H), int(W), int(M), int(device)
         self.h = self._L.dsrg_engine_create(self.device, self.max_batch, self.H, self.W, self.M)
         if not self.h:

@@ -138,6 +138,7 @@ extern "C" int dsrg_annotation_forward_dev(dsrg_engine *h, int B, const int32_t 
                                            const float *images_in_dev, int Hi, int Wi, float *labels_out_dev,
                                            float *cues_out_dev, float *images_out_dev, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     return annotation_forward(e, B, tag_offsets, tags, cue_offsets, cue_idx, flip, images_in_dev, Hi, Wi,
@@ -149,6 +150,7 @@ extern "C" int dsrg_annotation_forward_host(dsrg_engine *h, int B, const int32_t
                                             const float *images_in, int Hi, int Wi, float *labels_out,
                                             float *cues_out, float *images_out) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if ((rc = ensure_staging(e))) return rc;

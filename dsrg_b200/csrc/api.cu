@@ -5,7 +5,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
+#include <utility>
 #include <new>
 #include <vector>
 
@@ -183,7 +185,8 @@ int check_batch(Engine *e, int B) {
         set_error("batch %d outside [1, %d]", B, e->maxB);
         return DSRG_E_INVALID;
     }
-    DSRG_CUDA_TRY(cudaSetDevice(e->device));
+    int cur = -1;  // the entry point's DeviceScope selected the engine's device
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != e->device) DSRG_CUDA_TRY(cudaSetDevice(e->device));
     return DSRG_OK;
 }
 
@@ -239,6 +242,18 @@ int dsrg_device_count(void) {
     return n;
 }
 
+int dsrg_current_device(void) {
+    // the device the drop-ins create their engines on: DSRG_B200_DEVICE if set, else the calling thread's
+    // current CUDA device (what caffe.set_device / torch.cuda.set_device selected), else LOCAL_RANK
+    if (const char *ev = getenv("DSRG_B200_DEVICE")) return atoi(ev);
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return dev;
+}
+
 void *dsrg_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
@@ -271,6 +286,7 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
         return nullptr;
     }
     int ndev = 0;
+    if (device < 0) device = dsrg_current_device();  // -1: the calling thread's current device
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
         cudaGetLastError();
         set_error("no usable CUDA device %d (visible devices: %d): this library has no CPU fallback",
@@ -278,7 +294,10 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
         return nullptr;
     }
     cudaDeviceProp prop;
-    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    Engine probe;
+    probe.device = device;
+    DeviceScope dev_scope(&probe);  // creation, too, leaves the caller's current device as it found it
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         set_error("cannot select device %d", device);
         return nullptr;
     }
@@ -345,7 +364,7 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
 void dsrg_engine_destroy(dsrg_engine *h) {
     Engine *e = (Engine *)h;
     if (!e) return;
-    cudaSetDevice(e->device);
+    DeviceScope dev_scope(e);
     cudaDeviceSynchronize();
     lattice_free(e->sp);
     lattice_free(e->bi);
@@ -384,7 +403,7 @@ int dsrg_engine_set_size(dsrg_engine *h, int H, int W) {
     if (H == e->H && W == e->W) return DSRG_OK;
     // work already queued keeps the old strides in its launch arguments; wait for it before the
     // buffers are re-interpreted with the new ones
-    DSRG_CUDA_TRY(cudaSetDevice(e->device));
+    DeviceScope dev_scope(e);
     DSRG_CUDA_TRY(cudaDeviceSynchronize());
     engine_shape(e, H, W);
     return DSRG_OK;
@@ -444,7 +463,7 @@ int dsrg_engine_profile(dsrg_engine *h, int enable) {
 int dsrg_engine_profile_read(dsrg_engine *h, float *ms_out, long long *count_out) {
     Engine *e = (Engine *)h;
     if (!e || !ms_out || !count_out) return DSRG_E_INVALID;
-    DSRG_CUDA_TRY(cudaSetDevice(e->device));
+    DeviceScope dev_scope(e);
     DSRG_CUDA_TRY(cudaDeviceSynchronize());
     for (int t = 0; t < T_COUNT; t++) {
         ms_out[t] = 0.0f;
@@ -467,6 +486,7 @@ int dsrg_crf_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layo
                        const uint8_t *image, const dsrg_crf_params *params, float *out,
                        int out_layout, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!out || (out_layout != DSRG_LAYOUT_NHWC && out_layout != DSRG_LAYOUT_NCHW)) {
@@ -483,6 +503,7 @@ int dsrg_crf_map_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_
                            const uint8_t *image, const dsrg_crf_params *params, int32_t *labels_out,
                            void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!labels_out) {
@@ -499,6 +520,7 @@ int dsrg_crf_batch_host(dsrg_engine *h, int B, const float *unary, int unary_lay
                         const uint8_t *image, const dsrg_crf_params *params, float *out,
                         int out_layout) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!unary || !image || !out) {
@@ -520,6 +542,7 @@ int dsrg_srg_batch_dev(dsrg_engine *h, int B, const float *labels, const float *
                        const float *cues, double th1, double th2, int renorm, float *seeds_out,
                        int32_t *label_map_out, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!labels || !probs || !cues || !seeds_out) {
@@ -538,6 +561,7 @@ int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *pro
                           const float *cues, const uint8_t *image, const dsrg_crf_params *params,
                           double th1, double th2, float *seeds_out, float *crf_out, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!labels || !probs || !cues || !seeds_out) {
@@ -557,6 +581,7 @@ int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t
                               const dsrg_crf_params *params, float *log_out, float *result,
                               void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!probs || !log_out) {
@@ -572,6 +597,7 @@ int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t
 int dsrg_crflayer_forward_host(dsrg_engine *h, int B, float *probs, const uint8_t *image,
                                const dsrg_crf_params *params, float *log_out, float *result) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!probs || !image || !log_out) {
@@ -594,6 +620,7 @@ int dsrg_crflayer_forward_host(dsrg_engine *h, int B, float *probs, const uint8_
 int dsrg_seedloss_forward_host(dsrg_engine *h, int B, const float *probs, const float *seeds,
                                float *terms_out) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!probs || !seeds || !terms_out) {
@@ -614,6 +641,7 @@ int dsrg_seedloss_forward_host(dsrg_engine *h, int B, const float *probs, const 
 int dsrg_seedloss_backward_host(dsrg_engine *h, int B, int n_global, const float *probs,
                                 const float *seeds, float top_diff, float *grad) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!probs || !seeds || !grad || n_global < 1) {
@@ -634,6 +662,7 @@ int dsrg_seedloss_backward_host(dsrg_engine *h, int B, int n_global, const float
 int dsrg_seedloss_forward_dev(dsrg_engine *h, int B, const float *probs, const float *seeds,
                               float *terms_out, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!probs || !seeds || !terms_out) {
@@ -646,6 +675,7 @@ int dsrg_seedloss_forward_dev(dsrg_engine *h, int B, const float *probs, const f
 int dsrg_seedloss_backward_dev(dsrg_engine *h, int B, int n_global, const float *probs,
                                const float *seeds, float top_diff, float *grad, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!probs || !seeds || !grad || n_global < 1) {
@@ -657,6 +687,7 @@ int dsrg_seedloss_backward_dev(dsrg_engine *h, int B, int n_global, const float 
 
 int dsrg_engine_lattice_sizes(dsrg_engine *h, int B, int *v_spatial, int *v_bilateral) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     DSRG_CUDA_TRY(cudaDeviceSynchronize());
@@ -668,6 +699,7 @@ int dsrg_engine_lattice_sizes(dsrg_engine *h, int B, int *v_spatial, int *v_bila
 
 int dsrg_engine_copy_norm(dsrg_engine *h, int which, int B, float *norm_out) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     DSRG_CUDA_TRY(cudaDeviceSynchronize());
@@ -693,19 +725,21 @@ struct dsrg_densecrf {
 // host copies of their inputs only, and borrow a process-wide batch-1 engine per label count -- sized for the
 // largest image seen so far and re-shaped per call -- for the duration of inference()/map().
 static std::mutex g_pool_mu;
-static Engine *g_pool[DSRG_MAX_LABELS + 1] = {nullptr};
+static std::map<std::pair<int, int>, Engine *> g_pool;  // (device, label count) -> engine
 
 static Engine *pool_engine(int H, int W, int M) {   // call with g_pool_mu held
-    Engine *e = g_pool[M];
+    const int dev = dsrg_current_device();           // the caller's current device, like every drop-in
+    Engine *&slot = g_pool[std::make_pair(dev, M)];
+    Engine *e = slot;
     if (e && (H > e->Hcap || W > e->Wcap)) {
         H = H > e->Hcap ? H : e->Hcap;
         W = W > e->Wcap ? W : e->Wcap;
         dsrg_engine_destroy((dsrg_engine *)e);
-        e = g_pool[M] = nullptr;
+        e = slot = nullptr;
     }
     if (!e) {
         const int Hc = (H + 63) / 64 * 64, Wc = (W + 63) / 64 * 64;   // head-room for slightly larger images
-        e = g_pool[M] = (Engine *)dsrg_engine_create(0, 1, Hc, Wc, M);
+        e = slot = (Engine *)dsrg_engine_create(dev, 1, Hc, Wc, M);
         if (!e) return nullptr;
     }
     return e;
@@ -713,10 +747,9 @@ static Engine *pool_engine(int H, int W, int M) {   // call with g_pool_mu held
 
 void dsrg_densecrf_release_engines(void) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    for (auto &e : g_pool) {
-        if (e) dsrg_engine_destroy((dsrg_engine *)e);
-        e = nullptr;
-    }
+    for (auto &kv : g_pool)
+        if (kv.second) dsrg_engine_destroy((dsrg_engine *)kv.second);
+    g_pool.clear();
 }
 
 dsrg_densecrf *dsrg_densecrf_create(int W, int H, int nlabels) {
@@ -762,6 +795,12 @@ int dsrg_densecrf_add_pairwise_energy(dsrg_densecrf *c, float w1, float theta_al
         set_error("NULL pointer argument");
         return DSRG_E_INVALID;
     }
+    if (c->has_pairwise) {
+        // DenseCRFWrapper::add_pairwise_energy APPENDS a Gaussian and a bilateral term on every call
+        // (densecrf_wrapper.cpp:25-29); this object holds one pair, which is all CRF() ever adds (CRF.py:31-32)
+        set_error("add_pairwise_energy was already called on this object: only one Gaussian + bilateral pair is supported");
+        return DSRG_E_STATE;
+    }
     c->params.w1 = w1;
     c->params.theta_alpha_x = theta_alpha_1;
     c->params.theta_alpha_y = theta_alpha_2;
@@ -782,21 +821,24 @@ static int densecrf_run(dsrg_densecrf *c, int n_iters, Engine **eng) {
         set_error("NULL object");
         return DSRG_E_INVALID;
     }
-    if (!c->has_pairwise) {
-        set_error("add_pairwise_energy must be called before inference/map");
-        return DSRG_E_STATE;
-    }
     Engine *e = pool_engine(c->H, c->W, c->M);
     if (!e) return DSRG_E_CUDA;
     *eng = e;
+    DeviceScope dev_scope(e);
     int rc = dsrg_engine_set_size((dsrg_engine *)e, c->H, c->W);
     if (rc) return rc;
     if ((rc = ensure_staging(e))) return rc;
     if (!c->has_unary) c->unary.assign((size_t)c->W * c->H * c->M, 0.0f);  // unary.fill(0), densecrf.cpp:117
     c->params.n_iters = n_iters;
     cudaStream_t s = e->own_stream;
-    DSRG_CUDA_TRY(cudaSetDevice(e->device));
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, c->unary.data(), c->unary.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (!c->has_pairwise) {
+        // no pairwise term: every mean-field step reproduces Q = softmax(-unary) (densecrf.cpp:120-128 with an
+        // empty pairwise list), which is what the reference returns
+        dsrg_crf_params p0 = c->params;
+        p0.n_iters = 0;
+        return meanfield_run(e, 1, e->st_unary, DSRG_LAYOUT_NHWC, false, nullptr, p0, s);
+    }
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image, c->image.data(), c->image.size(), cudaMemcpyHostToDevice, s));
     return crf_core(e, 1, e->st_unary, DSRG_LAYOUT_NHWC, false, nullptr, e->st_image, &c->params, s);
 }
@@ -810,6 +852,7 @@ int dsrg_densecrf_inference(dsrg_densecrf *c, int n_iters, float *probs_out) {
     Engine *e = nullptr;
     int rc = densecrf_run(c, n_iters, &e);
     if (rc) return rc;
+    DeviceScope dev_scope(e);
     cudaStream_t s = e->own_stream;
     if ((rc = meanfield_export(e, 1, e->st_out, DSRG_LAYOUT_NHWC, s))) return rc;
     DSRG_CUDA_TRY(cudaMemcpyAsync(probs_out, e->st_out, c->unary.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -825,6 +868,7 @@ int dsrg_densecrf_map(dsrg_densecrf *c, int n_iters, int *labels) {
     Engine *e = nullptr;
     int rc = densecrf_run(c, n_iters, &e);
     if (rc) return rc;
+    DeviceScope dev_scope(e);
     cudaStream_t s = e->own_stream;
     if ((rc = meanfield_export_map(e, 1, e->st_lmap, s))) return rc;
     DSRG_CUDA_TRY(cudaMemcpyAsync(labels, e->st_lmap, (size_t)c->W * c->H * sizeof(int), cudaMemcpyDeviceToHost, s));

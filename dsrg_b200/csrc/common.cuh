@@ -202,6 +202,65 @@ struct LaunchScope {
     } while (0)
 
 
+// float64 sum of n values in the order NumPy adds a contiguous reduction axis (pairwise_sum in
+// numpy/core/src/umath/loops_utils.h.src: eight accumulators, their fixed combination tree, then the tail;
+// blocks of at most 128).  The reference renormalises with np.sum(result, axis=1) on a TRANSPOSED view of an
+// (N,H,W,C) float64 array (pylayers.py:328-330, :85-86), i.e. the class axis is the contiguous one and this is
+// the order its sum is formed in; for 21 classes it differs from a sequential sum in the last bit on ~17 % of
+// the pixels, which matters to the strict float64 threshold compares that follow (pylayers.py:251-257).
+// `get(i)` returns element i; NT > 0 makes n a compile-time constant.
+template <int NT, typename F>
+__device__ __forceinline__ double numpy_sum_block(F get, int lo, int n_rt) {
+    const int n = NT ? NT : n_rt;
+    if (n < 8) {
+        double res = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) res += get(lo + i);
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = get(lo + j);
+    int i = 8;
+#pragma unroll
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] += get(lo + i + j);
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (; i < n; i++) res += get(lo + i);
+    return res;
+}
+template <int NT, typename F>
+__device__ __forceinline__ double numpy_sum(F get, int n_rt) {
+    const int n = NT ? NT : n_rt;
+    if (n <= 128) return numpy_sum_block<NT>(get, 0, n);
+    int n2 = n / 2;  // n <= 255 here (DSRG_MAX_LABELS, SRG's 255): one level of the recursion
+    n2 -= n2 % 8;
+    return numpy_sum_block<0>(get, 0, n2) + numpy_sum_block<0>(get, n2, n - n2);
+}
+
+// Entry points run on the engine's device and hand the calling thread back on the device it came with: a Caffe
+// solver thread (or any host framework) keeps its own current device across a drop-in call.
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceScope(const Engine *e) {
+        if (!e) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+        if (prev != e->device) switched = cudaSetDevice(e->device) == cudaSuccess && prev >= 0;
+    }
+    ~DeviceScope() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceScope(const DeviceScope &) = delete;
+    DeviceScope &operator=(const DeviceScope &) = delete;
+};
+
 int device_alloc(Engine *e, void **p, size_t bytes);
 int check_batch(Engine *e, int B);
 int ensure_staging(Engine *e);

@@ -279,6 +279,7 @@ using namespace dsrg;
 static int host_elementwise(dsrg_engine *h, int B, const float *in0, const float *in1, float *out0, float *out1,
                             float *scalar_out, int op) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!in0 || (op != 0 && !in1)) {
@@ -307,24 +308,28 @@ static int host_elementwise(dsrg_engine *h, int B, const float *in0, const float
 extern "C" {
 int dsrg_softmax_forward_dev(dsrg_engine *h, int B, const float *preds, float *probs_out, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     return rc ? rc : softmax_forward(e, B, preds, probs_out, (cudaStream_t)stream);
 }
 int dsrg_softmax_backward_dev(dsrg_engine *h, int B, const float *preds, const float *top_diff, float *grad_out,
                               void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     return rc ? rc : softmax_backward(e, B, preds, top_diff, grad_out, (cudaStream_t)stream);
 }
 int dsrg_constrainloss_forward_dev(dsrg_engine *h, int B, const float *probs, const float *log_smooth,
                                    float *loss_out, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     return rc ? rc : constrain_forward(e, B, probs, log_smooth, loss_out, (cudaStream_t)stream);
 }
 int dsrg_constrainloss_backward_dev(dsrg_engine *h, int B, const float *probs, const float *log_smooth,
                                     float *grad_probs, float *grad_log, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     return rc ? rc : constrain_backward(e, B, probs, log_smooth, grad_probs, grad_log, (cudaStream_t)stream);
 }

@@ -549,12 +549,12 @@ k_mf_export_renorm(const float *Q, float *result_out, float *log_out, int M, int
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    double s = 0.0;
-    for (int k = 0; k < M; k++) {
-        double v = (double)Q[((size_t)b * M + k) * N + i];
-        if (v < 0.0001) v = 0.0001;
-        s += v;
-    }
+    // float64 sum in NumPy's order for the reference's layout (common.cuh:numpy_sum)
+    auto clamped = [&](int k) {
+        const double v = (double)Q[((size_t)b * M + k) * N + i];
+        return v < 0.0001 ? 0.0001 : v;
+    };
+    const double s = numpy_sum<0>(clamped, M);
     for (int k = 0; k < M; k++) {
         size_t at = ((size_t)b * M + k) * N + i;
         double v = (double)Q[at];

@@ -196,6 +196,7 @@ using namespace dsrg;
 extern "C" int dsrg_zoom_scores_dev(dsrg_engine *h, const float *scores_dev, int hi, int wi, float *out_dev,
                                     int accumulate, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, 1);
     if (rc) return rc;
     if (!scores_dev || !out_dev || hi < 1 || wi < 1) {
@@ -208,6 +209,7 @@ extern "C" int dsrg_zoom_scores_dev(dsrg_engine *h, const float *scores_dev, int
 extern "C" int dsrg_zoom_scores_host(dsrg_engine *h, const float *scores, int hi, int wi, float *out,
                                      int accumulate) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, 1);
     if (rc) return rc;
     if (!scores || !out || hi < 1 || wi < 1) {
@@ -232,6 +234,7 @@ extern "C" int dsrg_predict_mask_dev(dsrg_engine *h, int mode, int n_scales, con
                                      int smooth, const dsrg_crf_params *params, const int32_t *labels_sel,
                                      int n_sel, int32_t *result_out_dev, float *probs_out_dev, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, 1);
     if (rc) return rc;
     return predict_mask(e, mode, n_scales, scores_dev, hs, ws, image_dev, eps, smooth, params, labels_sel, n_sel,
@@ -243,6 +246,7 @@ extern "C" int dsrg_predict_mask_host(dsrg_engine *h, int mode, int n_scales, co
                                       const dsrg_crf_params *params, const int32_t *labels_sel, int n_sel,
                                       int32_t *result_out, float *probs_out) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, 1);
     if (rc) return rc;
     if (n_scales < 1 || n_scales > 16 || !scores || !hs || !ws || !result_out || (smooth && !image)) {

@@ -44,6 +44,7 @@ using namespace dsrg;
 extern "C" int dsrg_prepare_image_dev(dsrg_engine *h, int B, int Hi, int Wi, const float *images_dev,
                                       const double *mean_pixel, uint8_t *image_out_dev, void *stream) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!images_dev || !mean_pixel || !image_out_dev || Hi < 1 || Wi < 1) {
@@ -56,6 +57,7 @@ extern "C" int dsrg_prepare_image_dev(dsrg_engine *h, int B, int Hi, int Wi, con
 extern "C" int dsrg_prepare_image_host(dsrg_engine *h, int B, int Hi, int Wi, const float *images,
                                        const double *mean_pixel, uint8_t *image_out) {
     Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
     if (!images || !mean_pixel || !image_out || Hi < 1 || Wi < 1) {

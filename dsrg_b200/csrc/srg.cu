@@ -89,16 +89,21 @@ k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, c
                 cue_at_L = cu;
             }
             double v = (double)(MT ? pv[MT ? c : 0] : pb[(size_t)c * N]);
-            if (renorm) {
-                if (v < 0.0001) v = 0.0001;
-                s += v;  // sequential float64 sum over classes, like np.sum(axis=1)
-            }
+            if (renorm && v < 0.0001) v = 0.0001;
             if (lab[c] == 1.0f && (cstar < 0 || v > best)) {
                 best = v;
                 cstar = c;
             }
         }
-        if (renorm) best = best / s;
+        if (renorm) {
+            // float64 sum of the clamped values in NumPy's order (common.cuh:numpy_sum)
+            auto clamped = [&](int c) {
+                const double v = (double)(MT ? pv[MT ? c : 0] : pb[(size_t)c * N]);
+                return v < 0.0001 ? 0.0001 : v;
+            };
+            s = numpy_sum<MT>(clamped, M);
+            best = best / s;
+        }
         // thresholds (pylayers.py:251-257): strict > in float64; overwrite the seed label
         if (cstar >= 0 && best > th2 && (cstar != 0 || best > th1)) {
             L = cstar + 1;

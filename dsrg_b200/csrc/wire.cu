@@ -220,9 +220,31 @@ extern "C" void dsrg_wire_apply_clamp_mask(const uint32_t *src, float *probs, si
 }
 
 // srg_only: no CRF (probs are read-only, `renorm` as in dsrg_srg_batch_dev, optional label map out)
+static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *probs, const float *cues,
+                          const uint8_t *image, const dsrg_crf_params *params, double th1, double th2,
+                          float *seeds_out, float *crf_out, bool srg_only, int renorm, int32_t *label_map_out);
+
 static int host_pass(dsrg_engine *h, int B, const float *labels, float *probs, const float *cues,
                      const uint8_t *image, const dsrg_crf_params *params, double th1, double th2,
                      float *seeds_out, float *crf_out, bool srg_only, int renorm, int32_t *label_map_out) {
+    Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
+    const int rc = host_pass_impl(h, B, labels, probs, cues, image, params, th1, th2, seeds_out, crf_out, srg_only,
+                                  renorm, label_map_out);
+    if (rc != DSRG_OK && e && e->in_stream) {
+        // a chunk failed mid-pipeline: copies of earlier chunks may still be reading or writing the caller's
+        // buffers -- wait for them before the error is reported (the outputs are then undefined, not in flight)
+        cudaStreamSynchronize(e->in_stream);
+        cudaStreamSynchronize(e->own_stream);
+        cudaStreamSynchronize(e->out_stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *probs, const float *cues,
+                          const uint8_t *image, const dsrg_crf_params *params, double th1, double th2,
+                          float *seeds_out, float *crf_out, bool srg_only, int renorm, int32_t *label_map_out) {
     Engine *e = (Engine *)h;
     int rc = check_batch(e, B);
     if (rc) return rc;

@@ -29,10 +29,13 @@ _ENGINES = {}
 
 
 def _engine(n, c, h, w):
-    """One engine per blob shape, created on first use and kept (layers are long-lived)."""
-    key = (int(n), int(c), int(h), int(w))
+    """One engine per blob shape and device, created on first use and kept (layers are long-lived).  The device
+    is the solver thread's current CUDA device -- the one ``caffe.set_device`` chose (training/tools/train.py:77-79)
+    -- or DSRG_B200_DEVICE; every C entry point restores the thread's current device before it returns."""
+    from dsrg_b200 import _lib
+    key = (int(n), int(c), int(h), int(w), int(_lib.lib().dsrg_current_device()))
     if key not in _ENGINES:
-        _ENGINES[key] = _api.Engine(key[0], key[2], key[3], key[1])
+        _ENGINES[key] = _api.Engine(key[0], key[2], key[3], key[1], device=key[4])
     return _ENGINES[key]
 
 
@@ -98,11 +101,19 @@ class CRFLayer(caffe.Layer):
 
 
 class BalancedSeedLossLayer(caffe.Layer):
-    """pylayers.py:120-152."""
+    """pylayers.py:120-152.  Default = the reference's semantics: the mean over THIS solver's batch (one Caffe
+    solver per GPU, gradients averaged by the trainer).  ``param_str: "{'global_batch': True}"`` (or
+    DSRG_B200_GLOBAL_LOSS=1) opts into the mean over the global batch of a torch.distributed job instead: the two
+    local sums and the local image count are all-reduced once, in forward (dsrg_b200/shard.py); backward reuses
+    the count and issues no collective."""
 
     def setup(self, bottom, top):
         if len(bottom) != 2:
             raise Exception("The layer needs two inputs!")
+        import os
+        params = yaml.safe_load(self.param_str) if getattr(self, "param_str", "") else None
+        self._global = bool((params or {}).get("global_batch", os.environ.get("DSRG_B200_GLOBAL_LOSS", "0") == "1"))
+        self._n_global = None
 
     def reshape(self, bottom, top):
         top[0].reshape(1)
@@ -110,12 +121,15 @@ class BalancedSeedLossLayer(caffe.Layer):
     def forward(self, bottom, top):
         n, c, h, w = bottom[0].data.shape
         terms = _engine(n, c, h, w).seedloss_forward_host(_f32(bottom[0].data), _f32(bottom[1].data))
-        terms, n_global = _allreduce_terms(terms, n)
+        n_global = n
+        if self._global:
+            terms, n_global = _allreduce_terms(terms, n)
+        self._n_global = n_global
         top[0].data[...] = -(float(terms[0]) + float(terms[1])) / n_global
 
     def backward(self, top, prop_down, bottom):
         n, c, h, w = bottom[0].data.shape
-        _, n_global = _allreduce_terms(None, n)
+        n_global = self._n_global if (self._global and self._n_global) else n
         # like the reference (pylayers.py:150-152) the incoming top diff is NOT applied
         bottom[0].diff[...] = _engine(n, c, h, w).seedloss_backward_host(_f32(bottom[0].data), _f32(bottom[1].data),
                                                                            n_global=n_global, top_diff=1.0)

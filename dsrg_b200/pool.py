@@ -8,8 +8,12 @@ _ENGINES = {}      # (M, device) -> Engine
 _ROUND = 64        # capacity granularity, so that slightly larger images do not force a new engine
 
 
-def engine_for(H, W, M, device=0):
+def engine_for(H, W, M, device=None):
+    """device None: the calling thread's current CUDA device (dsrg_current_device)."""
     H, W, M = int(H), int(W), int(M)
+    if device is None:
+        from . import _lib
+        device = _lib.lib().dsrg_current_device()
     key = (M, int(device))
     eng = _ENGINES.get(key)
     if eng is not None:

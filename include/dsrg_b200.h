@@ -38,6 +38,11 @@ extern "C" {
 int dsrg_version(void);               /* 10000*major + 100*minor + patch */
 const char *dsrg_last_error(void);    /* message of the last failing call on this thread */
 int dsrg_device_count(void);          /* number of visible CUDA devices (0 if none / no driver) */
+/* The device an engine is created on when `device` is -1, and the one the drop-ins (pylayers, krahenbuhl2013,
+ * the DenseCRF objects) use: DSRG_B200_DEVICE if set, else the calling thread's current CUDA device -- what
+ * caffe.set_device(N) (training/tools/train.py:77-79) or torch.cuda.set_device selected.  -1 if there is none.
+ * Every entry point restores the caller's current device before it returns. */
+int dsrg_current_device(void);
 
 /* Pinned host memory so the *_host entry points overlap their copies (cudaHostAlloc). */
 void *dsrg_host_alloc(size_t bytes);
@@ -67,7 +72,7 @@ void dsrg_crf_params_default(dsrg_crf_params *p, float scale_factor, float color
 
 /* ------------------------------------------------------------------------------------------
  * Engine: owns every device buffer the batched kernels need for up to max_batch images of
- * H x W pixels and M labels on `device`.  No allocation happens on the hot calls.
+ * H x W pixels and M labels on `device` (-1: dsrg_current_device()).  No allocation happens on the hot calls.
  * ------------------------------------------------------------------------------------------ */
 typedef struct dsrg_engine dsrg_engine;
 

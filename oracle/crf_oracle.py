@@ -346,6 +346,23 @@ def zoom_order1_restated(im, oh, ow):
     return t.astype(im.dtype)
 
 
+def renormalise(q_nchw):
+    """pylayers.py:328-330 on raw float32 CRF marginals given as (N,C,H,W) or (C,H,W): the clamp and the
+    float64 renormalisation IN THE REFERENCE'S MEMORY LAYOUT -- ``result`` is an (N,H,W,C) float64 array seen
+    through a transposed view, so np.sum(axis=1) reduces the contiguous class axis with NumPy's pairwise order
+    (8 accumulators + tail), which differs from a sum over the outer axis of a planar array in the last bit."""
+    q = np.asarray(q_nchw)
+    single = q.ndim == 3
+    if single:
+        q = q[None]
+    result = np.zeros((q.shape[0], q.shape[2], q.shape[3], q.shape[1]))        # :323 (float64, N,H,W,C)
+    result[...] = np.transpose(q, (0, 2, 3, 1))                                  # :326 (float32 CRF output)
+    result = np.transpose(result, [0, 3, 1, 2])                                  # :328
+    result[result < MIN_PROB] = MIN_PROB                                         # :329
+    result = result / np.sum(result, axis=1, keepdims=True)                      # :330
+    return result[0] if single else result
+
+
 def refinement(probs, im, scale_factor=12.0):
     """DSRGLayer.refinement, pylayers.py:310-331.  Mutates ``probs`` in place like the reference
     (:312).  Returns the float64 N x C x h x w renormalised CRF marginals."""

@@ -109,8 +109,10 @@ def test_crf_error_paths(torch_cuda):
         eng.crf_dev(u[:2], im[:2], p, torch.empty_like(u[:2]))
     assert ei.value.code == -3
     c = api.DenseCRF(8, 8, 21)
-    with pytest.raises(api.DsrgError) as ei:      # inference before add_pairwise_energy
-        c.inference(1)
+    im8 = np.zeros(8 * 8 * 3, np.uint8)
+    c.add_pairwise_energy(10, 80, 80, 13, 13, 13, 3, 3, 3, im8)
+    with pytest.raises(api.DsrgError) as ei:      # a second pairwise pair is refused (the reference would append it)
+        c.add_pairwise_energy(10, 80, 80, 13, 13, 13, 3, 3, 3, im8)
     assert ei.value.code == -4
     eng.close()
 
@@ -265,3 +267,43 @@ def test_crf_against_the_reference_build_directly(torch_cuda, H, W, sf, img):
         top2 = np.sort(want.reshape(-1, 21), axis=1)[:, -2:]
         assert ((top2[:, 1] - top2[:, 0])[bad] <= 4e-4).all()
     eng.close()
+
+
+def test_densecrf_object_without_pairwise_and_second_pairwise_call(torch_cuda):
+    """DenseCRFWrapper semantics at the edges: with no pairwise term inference() is softmax(-unary) after any
+    number of iterations (densecrf.cpp:115-131 with an empty pairwise list) -- checked against the reference-built
+    oracle object; a second add_pairwise_energy (which the reference would APPEND, densecrf_wrapper.cpp:25-29) is
+    refused with a clear error instead of silently replacing the first."""
+    rng = np.random.RandomState(3)
+    H, W, M = 9, 7, 5
+    unary = rng.randn(H, W, M).astype(np.float32)
+    c = api.DenseCRF(W, H, M)
+    c.set_unary_energy(unary.ravel())
+    o = crf_oracle.DenseCRF(W, H, M)
+    o.set_unary_energy(unary.ravel())
+    for it in (0, 3):
+        got = c.inference(it).reshape(H, W, M)
+        np.testing.assert_allclose(got, o.inference(it).reshape(H, W, M), atol=2e-6)
+        assert np.array_equal(c.map(it), o.map(it))
+    im = synth.make_image(rng, H, W, "noise")
+    c.add_pairwise_energy(10, 80, 80, 13, 13, 13, 3, 3, 3, im.ravel())
+    with pytest.raises(api.DsrgError):
+        c.add_pairwise_energy(10, 80, 80, 13, 13, 13, 3, 3, 3, im.ravel())
+
+
+def test_entry_points_keep_the_callers_current_device(torch_cuda):
+    """a drop-in call must not leave the calling (solver) thread on another CUDA device."""
+    torch = torch_cuda
+    from dsrg_b200 import _lib
+    L = _lib.lib()
+    assert L.dsrg_current_device() == torch.cuda.current_device()
+    n = torch.cuda.device_count()
+    target = n - 1                       # another device when the box has more than one
+    eng = api.Engine(1, 16, 16, 21, device=target)
+    assert torch.cuda.current_device() == 0 and L.dsrg_current_device() == 0
+    b = synth.make_batch(1, 16, 16, start=5)
+    out = eng.crf_host(np.ascontiguousarray(np.transpose(b["probs"], (0, 2, 3, 1))), b["image"], api.crf_params(1.0))
+    assert np.isfinite(out).all()
+    assert torch.cuda.current_device() == 0 and L.dsrg_current_device() == 0
+    eng.close()
+    assert api.Engine(1, 8, 8, 3).device == 0   # default = the current device
