@@ -285,6 +285,14 @@ def run_b200(args, rank, local_rank, world):
                 if dist is not None:
                     dist.all_reduce(d_terms)   # the path's only collective: 2 floats
 
+    # a real stream (not the legacy default stream): repeated passes are then replayed as CUDA graphs
+    side = torch.cuda.Stream(device=dev)
+    _plain_step = step
+
+    def step():
+        with torch.cuda.stream(side):
+            _plain_step()
+
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
@@ -294,10 +302,10 @@ def run_b200(args, rank, local_rank, world):
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(side)   # events on the stream the kernels are launched on
         for _ in range(steps):
             fn()
-        e1.record()
+        e1.record(side)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         if dist is not None:

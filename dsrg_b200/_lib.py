@@ -46,6 +46,8 @@ SIGNATURES = {
     "dsrg_engine_get_size": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "dsrg_engine_set_host_chunk": (_i, [_vp, _i]),
     "dsrg_engine_set_lanes": (_i, [_vp, _i]),
+    "dsrg_engine_set_graphs": (_i, [_vp, _i]),
+    "dsrg_engine_graph_replays": (_ll, [_vp]),
     "dsrg_engine_take_launch_count": (_ll, [_vp]),
     "dsrg_crf_batch_dev": (_i, [_vp, _i, _vp, _i, _vp, _pp, _vp, _i, _vp]),
     "dsrg_crf_batch_host": (_i, [_vp, _i, _vp, _i, _vp, _pp, _vp, _i]),

@@ -114,6 +114,14 @@ class Engine(object):
     def set_host_chunk(self, images):
         check(self._L.dsrg_engine_set_host_chunk(self.h, int(images)))
 
+    def set_graphs(self, enable):
+        """CUDA-graph replay of repeated device passes (default on; needs a non-default stream)."""
+        check(self._L.dsrg_engine_set_graphs(self.h, int(bool(enable))))
+
+    @property
+    def graph_replays(self):
+        return int(self._L.dsrg_engine_graph_replays(self.h))
+
     def set_lanes(self, lanes):
         check(self._L.dsrg_engine_set_lanes(self.h, int(lanes)))
 

@@ -190,6 +190,18 @@ int check_batch(Engine *e, int B) {
     return DSRG_OK;
 }
 
+// a pass may be captured / replayed as a graph only when it does not have to (re)build the shared spatial lattice
+static bool spatial_ready(const Engine *e, const dsrg_crf_params *p) {
+    return p && e->sp_valid && e->sp.sigma[0] == p->theta_gamma_x && e->sp.sigma[1] == p->theta_gamma_y;
+}
+
+static GraphKey pass_key(const Engine *e, int entry, int B, const dsrg_crf_params *p) {
+    GraphKey k;
+    k.add(entry).add(B).add(e->H).add(e->W);
+    if (p) k.add(*p);
+    return k;
+}
+
 static int crf_core(Engine *e, int B, const float *unary, int layout, bool clamp, float *unary_rw,
                     const uint8_t *image, const dsrg_crf_params *p, cudaStream_t s) {
     if (!unary || !image || !p) {
@@ -256,7 +268,8 @@ int dsrg_current_device(void) {
 
 void *dsrg_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+    // on the NUMA node of the calling thread's current device when several ranks share the host (numa.cu)
+    if (numa_host_alloc(&p, bytes ? bytes : 16, dsrg_current_device()) != cudaSuccess) {
         set_error("cudaHostAlloc(%zu) failed", bytes);
         cudaGetLastError();
         return nullptr;
@@ -309,6 +322,10 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     Engine *e = new (std::nothrow) Engine();
     if (!e) return nullptr;
     e->device = device;
+    if (numa_wanted()) {  // several ranks on this host: keep this rank's host side next to its GPU
+        e->numa_node = numa_node_of_device(device);
+        numa_bind_thread(e->numa_node);
+    }
     e->maxB = max_batch;
     e->M = M;
     e->MP = (M + 3) / 4 * 4;
@@ -351,6 +368,7 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     if (!rc && cudaEventCreateWithFlags(&e->join_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
     if (const char *ev = getenv("DSRG_B200_LANES")) e->lanes = atoi(ev) == 2 ? 2 : 1;
     if (const char *ev = getenv("DSRG_B200_WIRE")) e->wire_compress = atoi(ev) != 0;
+    if (const char *ev = getenv("DSRG_B200_GRAPHS")) e->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("DSRG_B200_HOST_CHUNK")) e->host_chunk = atoi(ev) > 0 ? atoi(ev) : e->host_chunk;
     if (!rc && cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
     if (rc) {
@@ -366,6 +384,7 @@ void dsrg_engine_destroy(dsrg_engine *h) {
     if (!e) return;
     DeviceScope dev_scope(e);
     cudaDeviceSynchronize();
+    graph_clear(e);
     lattice_free(e->sp);
     lattice_free(e->bi);
     void *ptrs[] = {e->U, e->Q0, e->spA, e->spB, e->spC, e->biA, e->biB, e->biC, e->nvA, e->nvB, e->lmap,
@@ -406,6 +425,9 @@ int dsrg_engine_set_size(dsrg_engine *h, int H, int W) {
     DeviceScope dev_scope(e);
     DSRG_CUDA_TRY(cudaDeviceSynchronize());
     engine_shape(e, H, W);
+    // graphs are keyed by the shape and hold its strides; the few an engine keeps are cheap to rebuild, and the
+    // per-image callers that re-shape on every call see each shape too rarely to profit from them
+    graph_clear(e);
     return DSRG_OK;
 }
 
@@ -445,6 +467,20 @@ int dsrg_engine_set_host_chunk(dsrg_engine *h, int images) {
     e->host_chunk = images;
     return DSRG_OK;
 }
+
+int dsrg_engine_set_graphs(dsrg_engine *h, int enable) {
+    Engine *e = (Engine *)h;
+    if (!e) return DSRG_E_INVALID;
+    e->use_graphs = enable != 0;
+    if (!enable) {
+        DeviceScope dev_scope(e);
+        cudaDeviceSynchronize();
+        graph_clear(e);
+    }
+    return DSRG_OK;
+}
+
+long long dsrg_engine_graph_replays(const dsrg_engine *h) { return h ? ((const Engine *)h)->graph_replays : 0; }
 
 int dsrg_engine_set_lanes(dsrg_engine *h, int lanes) {
     Engine *e = (Engine *)h;
@@ -494,9 +530,13 @@ int dsrg_crf_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layo
         return DSRG_E_INVALID;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    rc = crf_core(e, B, unary, unary_layout, false, nullptr, image, params, s);
-    if (rc) return rc;
-    return meanfield_export(e, B, out, out_layout, s);
+    GraphKey key = pass_key(e, 1, B, params);
+    key.add(unary).add(unary_layout).add(image).add(out).add(out_layout);
+    return run_pass(e, s, key, spatial_ready(e, params), [&]() {
+        int r = crf_core(e, B, unary, unary_layout, false, nullptr, image, params, s);
+        if (r) return r;
+        return meanfield_export(e, B, out, out_layout, s);
+    });
 }
 
 int dsrg_crf_map_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layout,
@@ -511,9 +551,13 @@ int dsrg_crf_map_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_
         return DSRG_E_INVALID;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    rc = crf_core(e, B, unary, unary_layout, false, nullptr, image, params, s);
-    if (rc) return rc;
-    return meanfield_export_map(e, B, labels_out, s);
+    GraphKey key = pass_key(e, 2, B, params);
+    key.add(unary).add(unary_layout).add(image).add(labels_out);
+    return run_pass(e, s, key, spatial_ready(e, params), [&]() {
+        int r = crf_core(e, B, unary, unary_layout, false, nullptr, image, params, s);
+        if (r) return r;
+        return meanfield_export_map(e, B, labels_out, s);
+    });
 }
 
 int dsrg_crf_batch_host(dsrg_engine *h, int B, const float *unary, int unary_layout,
@@ -569,12 +613,16 @@ int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *pro
         return DSRG_E_INVALID;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    // refinement (pylayers.py:310-331): in-place clamp, unary = probs (NCHW), CRF
-    rc = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
-    if (rc) return rc;
-    if (crf_out && (rc = meanfield_export(e, B, crf_out, DSRG_LAYOUT_NCHW, s))) return rc;
-    // SRG on the raw marginals with the float64 clamp + renormalisation fused in (renorm = 1)
-    return srg_run(e, B, labels, e->Qcur, cues, th1, th2, 1, seeds_out, nullptr, s);
+    GraphKey key = pass_key(e, 3, B, params);
+    key.add(labels).add(probs).add(cues).add(image).add(th1).add(th2).add(seeds_out).add(crf_out);
+    return run_pass(e, s, key, spatial_ready(e, params), [&]() {
+        // refinement (pylayers.py:310-331): in-place clamp, unary = probs (NCHW), CRF
+        int r = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
+        if (r) return r;
+        if (crf_out && (r = meanfield_export(e, B, crf_out, DSRG_LAYOUT_NCHW, s))) return r;
+        // SRG on the raw marginals with the float64 clamp + renormalisation fused in (renorm = 1)
+        return srg_run(e, B, labels, e->Qcur, cues, th1, th2, 1, seeds_out, nullptr, s);
+    });
 }
 
 int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t *image,
@@ -589,9 +637,13 @@ int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t
         return DSRG_E_INVALID;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    rc = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
-    if (rc) return rc;
-    return meanfield_export_renorm(e, B, result, log_out, s);
+    GraphKey key = pass_key(e, 4, B, params);
+    key.add(probs).add(image).add(log_out).add(result);
+    return run_pass(e, s, key, spatial_ready(e, params), [&]() {
+        int r = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
+        if (r) return r;
+        return meanfield_export_renorm(e, B, result, log_out, s);
+    });
 }
 
 int dsrg_crflayer_forward_host(dsrg_engine *h, int B, float *probs, const uint8_t *image,

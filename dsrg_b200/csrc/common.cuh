@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <map>
+#include <string>
 #include <vector>
 
 #include "../../include/dsrg_b200.h"
@@ -116,6 +118,7 @@ int seedloss_backward(Engine *e, int B, int n_global, const float *probs, const 
 
 struct Engine {
     int device = 0;
+    int numa_node = -1;  // node of the GPU when host-side placement is on (numa.cu), else -1
     int maxB = 0, H = 0, W = 0, M = 0, MP = 0, N = 0;
     int Hcap = 0, Wcap = 0, Ncap = 0;  // shape the buffers were sized for (H <= Hcap, W <= Wcap)
     int sm_count = 148;
@@ -159,6 +162,12 @@ struct Engine {
     uint32_t *h_cbits = nullptr, *h_sbits = nullptr, *h_mbits = nullptr;
     int wire_compress = 1;
     int *dev_err = nullptr;  // device-side error flag
+    // CUDA graphs of whole device passes, keyed by everything a pass's launch arguments depend on (graph.cu)
+    struct GraphRec { cudaGraphExec_t exec = nullptr; long long launches = 0; unsigned long long last_use = 0; bool bad = false; };
+    std::map<std::string, GraphRec> graphs;
+    unsigned long long graph_clock = 0;
+    int use_graphs = 1;
+    long long graph_replays = 0;
     // per-kernel event timing (off by default)
     bool prof = false;
     struct ProfRec { int tag; cudaEvent_t a, b; };
@@ -260,6 +269,48 @@ struct DeviceScope {
     DeviceScope(const DeviceScope &) = delete;
     DeviceScope &operator=(const DeviceScope &) = delete;
 };
+
+// ---- numa.cu: host-side placement for one-process-per-GPU jobs ----
+bool numa_wanted();
+int numa_node_of_device(int device);
+bool numa_bind_thread(int node);
+bool numa_prefer_memory(int node);
+cudaError_t numa_host_alloc(void **p, size_t bytes, int device);
+
+// ---- graph.cu: replay a device pass as one CUDA graph ----
+// A pass (lattice build + mean-field loop + SRG ...) is 40-130 dependent launches whose arguments depend only on
+// the call's arguments; `key` holds all of them.  First sighting of a key: run eagerly.  Second: capture the same
+// launches from the stream into a graph, instantiate, launch.  Afterwards: one cudaGraphLaunch.  Falls back to
+// plain launches on the legacy default stream, inside somebody else's capture, while per-kernel profiling is on,
+// or if capture fails.  `body` issues the launches on `s` and returns a DSRG_* code.
+struct GraphKey {
+    std::string bytes;
+    template <typename T>
+    GraphKey &add(const T &v) {
+        bytes.append(reinterpret_cast<const char *>(&v), sizeof(T));
+        return *this;
+    }
+};
+constexpr int kGraphRetry = 1;  // graph_end: the capture could not be turned into a graph, issue the launches again
+int graph_begin(Engine *e, cudaStream_t s, const GraphKey &key, bool *captured);   // 1: replayed (skip body), 0: run body
+int graph_end(Engine *e, cudaStream_t s, const GraphKey &key, bool captured, int body_rc, long long launches_before);
+void graph_clear(Engine *e);
+template <typename F>
+inline int run_pass(Engine *e, cudaStream_t s, const GraphKey &key, bool allow_graph, F body) {
+    if (!allow_graph) return body();
+    bool cap = false;
+    const long long l0 = e->launches;
+    const int g = graph_begin(e, s, key, &cap);
+    if (g != 0) return g < 0 ? g : DSRG_OK;
+    int rc = body();
+    if (!cap) return rc;
+    rc = graph_end(e, s, key, cap, rc, l0);
+    if (rc == kGraphRetry) {
+        e->launches = l0;
+        rc = body();
+    }
+    return rc;
+}
 
 int device_alloc(Engine *e, void **p, size_t bytes);
 int check_batch(Engine *e, int B);

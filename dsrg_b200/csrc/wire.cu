@@ -189,9 +189,9 @@ static int ensure_wire(Engine *e) {
     rc |= dalloc(e, &e->d_sbits, n);
     rc |= dalloc(e, &e->d_mbits, n);
     if (rc) return DSRG_E_NOMEM;
-    DSRG_CUDA_TRY(cudaHostAlloc((void **)&e->h_cbits, n * 4, cudaHostAllocDefault));
-    DSRG_CUDA_TRY(cudaHostAlloc((void **)&e->h_sbits, n * 4, cudaHostAllocDefault));
-    DSRG_CUDA_TRY(cudaHostAlloc((void **)&e->h_mbits, n * 4, cudaHostAllocDefault));
+    DSRG_CUDA_TRY(numa_host_alloc((void **)&e->h_cbits, n * 4, e->device));
+    DSRG_CUDA_TRY(numa_host_alloc((void **)&e->h_sbits, n * 4, e->device));
+    DSRG_CUDA_TRY(numa_host_alloc((void **)&e->h_mbits, n * 4, e->device));
     return DSRG_OK;
 }
 
@@ -278,11 +278,13 @@ static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *pro
         }
     }
     if (cb0.empty()) {
-        // default: B/8, 3B/8, B/2 (8 | 24 | 32 of 64: measured best of the schedules tried -- a short first
-        // chunk gets the GPU going, big later chunks keep its kernels efficient); a positive host_chunk
-        // caps the chunk size instead
+        // default: B/16, 3B/16, then quarters (4 | 12 | 16 | 16 | 16 of 64).  The GPU is the slower stage of the
+        // pipeline (0.5 ms + 0.235 ms per image and chunk against 0.17 ms per image of PCIe at 321x321x21), so a
+        // short first chunk gets it going early and the rest must be big enough to keep its kernels efficient:
+        // measured best of the schedules in profiles/r2_host_schedule_sweep.txt once a chunk's ~130 launches are
+        // replayed as one CUDA graph (round 1, plain launches: 8 | 24 | 32).  A positive host_chunk caps the size.
         const int cap = e->host_chunk > 0 ? e->host_chunk : B;
-        const int want[3] = {(B + 7) / 8, (3 * B + 7) / 8, B};
+        const int want[3] = {(B + 15) / 16, (3 * B + 15) / 16, (B + 3) / 4};
         for (int b = 0, k = 0; b < B; k++) {
             int nb = want[k < 2 ? k : 2];
             if (nb > cap) nb = cap;
@@ -316,12 +318,18 @@ static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *pro
     };
     mark(s_in);  // time origin
     double t_pack = 0, t_unpack = 0, t_issue = 0, t_wait = 0, t0 = omp_get_wtime();
+    // what travels as bits is decided per chunk: bit 0 cues (host packs), bit 1 seeds (host unpacks), bit 2 the
+    // clamp mask of probs (host applies sparse writes -- cheap even with one or two threads, and it replaces a
+    // full float D2H of the probs blob)
+    enum { W_CUES = 1, W_SEEDS = 2, W_MASK = 4 };
+    const bool many_threads = wire_worthwhile();
     auto finish_chunk = [&](int c) {  // host side of a finished chunk
         const int b0 = cb0[c], nb = cnb[c];
-        if (!packed[c]) return;
+        if (!(packed[c] & (W_SEEDS | W_MASK))) return;
         const double tu = omp_get_wtime();
-        unpack_planes(e->h_sbits + (size_t)b0 * wpi, seeds_out + (size_t)b0 * img_elems,
-                      srg_only ? nullptr : e->h_mbits + (size_t)b0 * wpi, probs + (size_t)b0 * img_elems, img_elems, wpi, nb);
+        unpack_planes((packed[c] & W_SEEDS) ? e->h_sbits + (size_t)b0 * wpi : nullptr, seeds_out + (size_t)b0 * img_elems,
+                      (packed[c] & W_MASK) ? e->h_mbits + (size_t)b0 * wpi : nullptr, probs + (size_t)b0 * img_elems,
+                      img_elems, wpi, nb);
         t_unpack += omp_get_wtime() - tu;
     };
     for (int c = 0; c < nchunks; c++) {
@@ -336,11 +344,13 @@ static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *pro
         t_issue += omp_get_wtime() - ti;
         // ---- host: pack this chunk's cues (1 bit per value) unless they are not a 0/1 mask
         const double tp = omp_get_wtime();
-        const bool ok = e->wire_compress != 0 && wire_worthwhile() &&
+        const bool ok = e->wire_compress != 0 && many_threads &&
                         pack_mask(cues + (size_t)b0 * img_elems, e->h_cbits + (size_t)b0 * wpi, img_elems, wpi, nb);
+        const bool ok_s = e->wire_compress != 0 && many_threads;
+        const bool ok_m = e->wire_compress != 0 && !srg_only;
         t_pack += omp_get_wtime() - tp;
         ti = omp_get_wtime();
-        packed[c] = ok ? 1 : 0;
+        packed[c] = (char)((ok ? W_CUES : 0) | (ok_s ? W_SEEDS : 0) | (ok_m ? W_MASK : 0));
         if (ok)
             DSRG_CUDA_TRY(cudaMemcpyAsync(e->d_cbits + (size_t)b0 * wpi, e->h_cbits + (size_t)b0 * wpi,
                                           (size_t)nb * wpi * 4, cudaMemcpyHostToDevice, s_in));
@@ -355,13 +365,12 @@ static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *pro
         DSRG_CUDA_TRY(cudaStreamWaitEvent(s, e->pipe_events[3 * c], 0));
         mark(s);
         dim3 gb(cdiv(n_img, kThreads), nb);
-        if (ok) {
+        if (ok)
             DSRG_LAUNCH(e, T_WIRE, s,
                         k_bits_to_float<<<gb, kThreads, 0, s>>>(e->d_cbits + (size_t)b0 * wpi, e->st_cues + o, n_img, (int)wpi));
-            if (!srg_only)
-                DSRG_LAUNCH(e, T_WIRE, s,
-                            k_float_to_bits<1><<<gb, kThreads, 0, s>>>(e->st_unary + o, e->d_mbits + (size_t)b0 * wpi, n_img, (int)wpi));
-        }
+        if (ok_m)  // before the pass clamps the device copy in place
+            DSRG_LAUNCH(e, T_WIRE, s,
+                        k_float_to_bits<1><<<gb, kThreads, 0, s>>>(e->st_unary + o, e->d_mbits + (size_t)b0 * wpi, n_img, (int)wpi));
         if (srg_only)
             rc = dsrg_srg_batch_dev(h, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o, th1, th2,
                                     renorm, e->st_out + o, label_map_out ? e->st_lmap + (size_t)b0 * e->N : nullptr, s);
@@ -369,7 +378,7 @@ static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *pro
             rc = dsrg_dsrg_forward_dev(h, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o,
                                        e->st_image + (size_t)b0 * e->N * 3, params, th1, th2, e->st_out + o, nullptr, s);
         if (rc) return rc;
-        if (ok)
+        if (ok_s)
             DSRG_LAUNCH(e, T_WIRE, s,
                         k_float_to_bits<0><<<gb, kThreads, 0, s>>>(e->st_out + o, e->d_sbits + (size_t)b0 * wpi, n_img, (int)wpi));
         if (crf_out) {  // raw marginals of this chunk, parked in the (now consumed) cues staging area
@@ -379,18 +388,17 @@ static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *pro
         mark(s);
         // ---- D2H
         DSRG_CUDA_TRY(cudaStreamWaitEvent(s_out, e->pipe_events[3 * c + 1], 0));
-        if (ok) {
+        if (ok_s)
             DSRG_CUDA_TRY(cudaMemcpyAsync(e->h_sbits + (size_t)b0 * wpi, e->d_sbits + (size_t)b0 * wpi,
                                           (size_t)nb * wpi * 4, cudaMemcpyDeviceToHost, s_out));
-            if (!srg_only)
-                DSRG_CUDA_TRY(cudaMemcpyAsync(e->h_mbits + (size_t)b0 * wpi, e->d_mbits + (size_t)b0 * wpi,
-                                              (size_t)nb * wpi * 4, cudaMemcpyDeviceToHost, s_out));
-        } else {
+        else
             DSRG_CUDA_TRY(cudaMemcpyAsync(seeds_out + o, e->st_out + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-            // the reference mutates the probs blob in place (pylayers.py:312): hand the clamped values back
-            if (!srg_only)
-                DSRG_CUDA_TRY(cudaMemcpyAsync(probs + o, e->st_unary + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-        }
+        // the reference mutates the probs blob in place (pylayers.py:312): hand the clamp back, as a mask or whole
+        if (ok_m)
+            DSRG_CUDA_TRY(cudaMemcpyAsync(e->h_mbits + (size_t)b0 * wpi, e->d_mbits + (size_t)b0 * wpi,
+                                          (size_t)nb * wpi * 4, cudaMemcpyDeviceToHost, s_out));
+        else if (!srg_only)
+            DSRG_CUDA_TRY(cudaMemcpyAsync(probs + o, e->st_unary + o, n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         if (label_map_out)
             DSRG_CUDA_TRY(cudaMemcpyAsync(label_map_out + (size_t)b0 * e->N, e->st_lmap + (size_t)b0 * e->N,
                                           (size_t)nb * e->N * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));

@@ -91,7 +91,14 @@ int dsrg_engine_set_host_chunk(dsrg_engine *e, int images);
  * streams so that the DRAM-latency-bound blur passes of one half overlap the shared-memory-bound tile
  * kernel of the other (measured on B200: +1 %, so it is off by default). */
 int dsrg_engine_set_lanes(dsrg_engine *e, int lanes);
-/* Kernel launches issued by this engine since the last call (bench.py's gpu_launches). */
+/* Device passes (*_dev entry points, and through them the chunks of the *_host ones) are captured into CUDA
+ * graphs the second time a pass is issued with the same arguments and replayed afterwards -- one launch instead
+ * of 40-130 dependent ones.  Needs a real stream (not the legacy default stream); enable = 0 turns it off and
+ * drops the cached graphs (also: environment DSRG_B200_GRAPHS=0).  graph_replays counts the passes replayed. */
+int dsrg_engine_set_graphs(dsrg_engine *e, int enable);
+long long dsrg_engine_graph_replays(const dsrg_engine *e);
+/* Kernel launches issued by this engine since the last call (bench.py's gpu_launches); the kernels inside a
+ * replayed graph are counted. */
 long long dsrg_engine_take_launch_count(dsrg_engine *e);
 
 /*

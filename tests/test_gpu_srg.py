@@ -191,3 +191,50 @@ def test_srg_adversarial_connectivity(torch_cuda):
         assert np.array_equal(got[i], want), name
         grown = got[i, 5] > 0
         assert not (grown & ~m).any(), name
+
+
+def test_graph_replay_matches_plain_launches(torch_cuda):
+    """Repeated device passes are replayed as CUDA graphs (csrc/graph.cu): same seeds bit for bit, marginals within
+    the atomics' run-to-run noise, replays really happen on a side stream and never on the legacy default stream,
+    and a call with other arguments in between does not disturb a cached graph."""
+    torch = torch_cuda
+    B, H, W, M = 3, 41, 41, 21
+    batch = synth.make_batch(B, H, W, cues="cam", image="smooth", start=40)
+    eng = api.Engine(B, H, W, M)
+    params = api.crf_params(12.0)
+    d = {k: torch.from_numpy(batch[k]).cuda() for k in ("labels", "cues", "image")}
+    probs0 = torch.from_numpy(batch["probs"]).cuda()
+
+    def run(th2=0.85):
+        p = probs0.clone()
+        seeds, q = torch.empty_like(p), torch.empty_like(p)
+        eng.dsrg_forward_dev(d["labels"], p, d["cues"], d["image"], params, 0.99, th2, seeds, crf_out=q)
+        return p, seeds, q
+
+    eng.set_graphs(False)
+    _, s_ref, q_ref = run()
+    torch.cuda.synchronize()
+    eng.set_graphs(True)
+    run()                                   # legacy default stream: never captured
+    assert eng.graph_replays == 0
+    side = torch.cuda.Stream()
+    bufs = None
+    with torch.cuda.stream(side):
+        # identical pointers are what makes a pass repeatable: reuse the same tensors
+        p = probs0.clone()
+        seeds, q = torch.empty_like(p), torch.empty_like(p)
+        outs = []
+        for i in range(5):
+            p.copy_(probs0)
+            eng.dsrg_forward_dev(d["labels"], p, d["cues"], d["image"], params, 0.99, 0.85, seeds, crf_out=q)
+            if i == 2:   # a different threshold in between: its own key, runs eagerly
+                s2 = torch.empty_like(p)
+                eng.dsrg_forward_dev(d["labels"], p.clone(), d["cues"], d["image"], params, 0.99, 0.5, s2)
+            outs.append((seeds.clone(), q.clone()))
+    torch.cuda.synchronize()
+    assert eng.graph_replays >= 3            # sightings 2..5 of the same key: one capture + replays
+    for s_i, q_i in outs:
+        assert (q_i - q_ref).abs().max().item() <= 2e-5
+        assert torch.equal(s_i, s_ref) or (s_i != s_ref).sum().item() <= 2   # threshold ties under atomics noise
+    assert eng.take_launch_count() > 5 * 100   # replayed kernels are counted
+    eng.close()
