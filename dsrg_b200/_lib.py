@@ -37,6 +37,8 @@ SIGNATURES = {
     "dsrg_device_count": (_i, []),
     "dsrg_current_device": (_i, []),
     "dsrg_host_alloc": (_vp, [_sz]),
+    "dsrg_host_register": (_i, [_vp, _sz]),
+    "dsrg_host_unregister": (_i, [_vp]),
     "dsrg_host_free": (None, [_vp]),
     "dsrg_crf_params_default": (None, [_pp, _f, _f, _i]),
     "dsrg_engine_create": (_vp, [_i, _i, _i, _i, _i]),
@@ -77,6 +79,8 @@ SIGNATURES = {
     "dsrg_wire_unpack_mask": (None, [_vp, _vp, _sz]),
     "dsrg_wire_apply_clamp_mask": (None, [_vp, _vp, _sz]),
     "dsrg_crflayer_forward_host": (_i, [_vp, _i, _vp, _vp, _pp, _vp, _vp]),
+    "dsrg_srg_last_crf_host": (_i, [_vp, _i, _vp, _vp, _d, _d, _vp]),
+    "dsrg_crf_last_marginals_host": (_i, [_vp, _i, _vp, _i]),
     "dsrg_seedloss_forward_host": (_i, [_vp, _i, _vp, _vp, _vp]),
     "dsrg_seedloss_backward_host": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp]),
     "dsrg_seedloss_forward_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),

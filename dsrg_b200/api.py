@@ -250,6 +250,22 @@ class Engine(object):
                                                  C.byref(params), _hptr(log_out, np.float32), _hptr(result, np.float32)))
         return log_out
 
+    def srg_last_crf_host(self, labels, cues, th1, th2, seeds_out=None):
+        """SRG on the marginals of this engine's last CRF pass (one refinement, two consumers)."""
+        B = cues.shape[0]
+        if seeds_out is None:
+            seeds_out = np.empty(cues.shape, np.float32)
+        check(self._L.dsrg_srg_last_crf_host(self.h, B, _hptr(labels, np.float32), _hptr(cues, np.float32),
+                                             float(th1), float(th2), _hptr(seeds_out, np.float32)))
+        return seeds_out
+
+    def crf_last_marginals_host(self, B, layout=None):
+        layout = _lib.LAYOUT_NCHW if layout is None else layout
+        shape = (B, self.M, self.H, self.W) if layout == _lib.LAYOUT_NCHW else (B, self.H, self.W, self.M)
+        out = np.empty(shape, np.float32)
+        check(self._L.dsrg_crf_last_marginals_host(self.h, B, _hptr(out, np.float32), int(layout)))
+        return out
+
     def seedloss_forward_host(self, probs, seeds):
         """(term_bg, term_fg) local sums; loss = -(term_bg + term_fg) / N_global."""
         terms = np.zeros(2, np.float32)

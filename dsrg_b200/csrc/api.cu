@@ -195,6 +195,17 @@ static bool spatial_ready(const Engine *e, const dsrg_crf_params *p) {
     return p && e->sp_valid && e->sp.sigma[0] == p->theta_gamma_x && e->sp.sigma[1] == p->theta_gamma_y;
 }
 
+// after a replayed pass the host-side notes a live pass would have left must be there too
+static int crf_pass_done(Engine *e, int B, int rc) {
+    if (rc == DSRG_OK) {
+        e->Qcur = e->Q0;
+        e->last_crf_B = B;
+    } else {
+        e->last_crf_B = 0;
+    }
+    return rc;
+}
+
 static GraphKey pass_key(const Engine *e, int entry, int B, const dsrg_crf_params *p) {
     GraphKey k;
     k.add(entry).add(B).add(e->H).add(e->W);
@@ -279,6 +290,25 @@ void *dsrg_host_alloc(size_t bytes) {
 
 void dsrg_host_free(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+int dsrg_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return DSRG_E_INVALID;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostRegister(%zu bytes) failed", bytes);
+        return DSRG_E_CUDA;
+    }
+    return DSRG_OK;
+}
+
+int dsrg_host_unregister(void *p) {
+    if (!p) return DSRG_E_INVALID;
+    if (cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return DSRG_E_CUDA;
+    }
+    return DSRG_OK;
 }
 
 void dsrg_crf_params_default(dsrg_crf_params *p, float scale_factor, float color_factor, int maxiter) {
@@ -425,6 +455,7 @@ int dsrg_engine_set_size(dsrg_engine *h, int H, int W) {
     DeviceScope dev_scope(e);
     DSRG_CUDA_TRY(cudaDeviceSynchronize());
     engine_shape(e, H, W);
+    e->last_crf_B = 0;
     // graphs are keyed by the shape and hold its strides; the few an engine keeps are cheap to rebuild, and the
     // per-image callers that re-shape on every call see each shape too rarely to profit from them
     graph_clear(e);
@@ -532,11 +563,11 @@ int dsrg_crf_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layo
     cudaStream_t s = (cudaStream_t)stream;
     GraphKey key = pass_key(e, 1, B, params);
     key.add(unary).add(unary_layout).add(image).add(out).add(out_layout);
-    return run_pass(e, s, key, spatial_ready(e, params), [&]() {
+    return crf_pass_done(e, B, run_pass(e, s, key, spatial_ready(e, params), [&]() {
         int r = crf_core(e, B, unary, unary_layout, false, nullptr, image, params, s);
         if (r) return r;
         return meanfield_export(e, B, out, out_layout, s);
-    });
+    }));
 }
 
 int dsrg_crf_map_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layout,
@@ -553,11 +584,11 @@ int dsrg_crf_map_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_
     cudaStream_t s = (cudaStream_t)stream;
     GraphKey key = pass_key(e, 2, B, params);
     key.add(unary).add(unary_layout).add(image).add(labels_out);
-    return run_pass(e, s, key, spatial_ready(e, params), [&]() {
+    return crf_pass_done(e, B, run_pass(e, s, key, spatial_ready(e, params), [&]() {
         int r = crf_core(e, B, unary, unary_layout, false, nullptr, image, params, s);
         if (r) return r;
         return meanfield_export_map(e, B, labels_out, s);
-    });
+    }));
 }
 
 int dsrg_crf_batch_host(dsrg_engine *h, int B, const float *unary, int unary_layout,
@@ -615,14 +646,14 @@ int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *pro
     cudaStream_t s = (cudaStream_t)stream;
     GraphKey key = pass_key(e, 3, B, params);
     key.add(labels).add(probs).add(cues).add(image).add(th1).add(th2).add(seeds_out).add(crf_out);
-    return run_pass(e, s, key, spatial_ready(e, params), [&]() {
+    return crf_pass_done(e, B, run_pass(e, s, key, spatial_ready(e, params), [&]() {
         // refinement (pylayers.py:310-331): in-place clamp, unary = probs (NCHW), CRF
         int r = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
         if (r) return r;
         if (crf_out && (r = meanfield_export(e, B, crf_out, DSRG_LAYOUT_NCHW, s))) return r;
         // SRG on the raw marginals with the float64 clamp + renormalisation fused in (renorm = 1)
         return srg_run(e, B, labels, e->Qcur, cues, th1, th2, 1, seeds_out, nullptr, s);
-    });
+    }));
 }
 
 int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t *image,
@@ -639,11 +670,58 @@ int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t
     cudaStream_t s = (cudaStream_t)stream;
     GraphKey key = pass_key(e, 4, B, params);
     key.add(probs).add(image).add(log_out).add(result);
-    return run_pass(e, s, key, spatial_ready(e, params), [&]() {
+    return crf_pass_done(e, B, run_pass(e, s, key, spatial_ready(e, params), [&]() {
         int r = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
         if (r) return r;
         return meanfield_export_renorm(e, B, result, log_out, s);
-    });
+    }));
+}
+
+// ---- one refinement, two consumers (train-s.prototxt:758-786: CRFLayer and DSRGLayer read the same blobs) ----
+int dsrg_srg_last_crf_host(dsrg_engine *h, int B, const float *labels, const float *cues, double th1, double th2,
+                           float *seeds_out) {
+    Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!labels || !cues || !seeds_out) {
+        set_error("NULL pointer argument");
+        return DSRG_E_INVALID;
+    }
+    if (e->last_crf_B != B) {
+        set_error("no mean-field result for a batch of %d is held by this engine (last: %d)", B, e->last_crf_B);
+        return DSRG_E_STATE;
+    }
+    if ((rc = ensure_staging(e))) return rc;
+    cudaStream_t s = e->own_stream;
+    const size_t n = (size_t)B * e->M * e->N;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_labels, labels, (size_t)B * e->M * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, cues, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    // SRG on the raw marginals of the last pass, float64 clamp + renormalisation fused in (pylayers.py:328-344)
+    if ((rc = srg_run(e, B, e->st_labels, e->Qcur, e->st_cues, th1, th2, 1, e->st_out, nullptr, s))) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(seeds_out, e->st_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    return check_device_flag(e, s);
+}
+
+int dsrg_crf_last_marginals_host(dsrg_engine *h, int B, float *out, int out_layout) {
+    Engine *e = (Engine *)h;
+    DeviceScope dev_scope(e);
+    int rc = check_batch(e, B);
+    if (rc) return rc;
+    if (!out || (out_layout != DSRG_LAYOUT_NHWC && out_layout != DSRG_LAYOUT_NCHW)) {
+        set_error("bad output argument");
+        return DSRG_E_INVALID;
+    }
+    if (e->last_crf_B != B) {
+        set_error("no mean-field result for a batch of %d is held by this engine (last: %d)", B, e->last_crf_B);
+        return DSRG_E_STATE;
+    }
+    if ((rc = ensure_staging(e))) return rc;
+    cudaStream_t s = e->own_stream;
+    if ((rc = meanfield_export(e, B, e->st_out, out_layout, s))) return rc;
+    DSRG_CUDA_TRY(cudaMemcpyAsync(out, e->st_out, (size_t)B * e->M * e->N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DSRG_CUDA_TRY(cudaStreamSynchronize(s));
+    return DSRG_OK;
 }
 
 int dsrg_crflayer_forward_host(dsrg_engine *h, int B, float *probs, const uint8_t *image,

@@ -131,6 +131,7 @@ struct Engine {
     // mean-field state, planar [B][M][N]
     float *U = nullptr, *Q0 = nullptr;
     float *Qcur = nullptr;  // where the current marginals live
+    int last_crf_B = 0;     // images whose raw marginals of the last mean-field pass are still in Qcur (0: none)
     // lattice value buffers [rows][MP]
     float *spA = nullptr, *spB = nullptr, *spC = nullptr, *biA = nullptr, *biB = nullptr, *biC = nullptr;
     int tiles_x = 0, tiles_y = 0, ntiles = 0;  // tiles of tile_w x 8 pixels

@@ -654,6 +654,7 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
                     k_mf_init<MP><<<gp, kThreads, 0, s>>>(unary, unary_rw, layout, clamp ? 1 : 0, e->U,
                                                           T == 0 ? e->Q0 : nullptr, M, N));
     e->Qcur = e->Q0;
+    e->last_crf_B = B;  // host-side bookkeeping for dsrg_srg_last_crf_host (the launches below are already ordered on s)
     if (T == 0) return DSRG_OK;
     const float alpha_sp = 1.0f / (1 + powf(2, -e->sp.d));  // permutohedral.cpp:571
     const float alpha_bi = 1.0f / (1 + powf(2, -e->bi.d));

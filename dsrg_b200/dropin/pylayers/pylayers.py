@@ -43,17 +43,66 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+_PINNED_REGIONS = {}   # data pointer -> nbytes of blob buffers page-locked with dsrg_host_register
+
+
+def _pin(a):
+    """Page-lock a blob's buffer once (Caffe keeps its blobs for the life of the net; in GPU mode their CPU side
+    already is pinned memory): the host entry points then stream it at the PCIe rate instead of going through the
+    driver's staged pageable copies.  DSRG_B200_PIN_BLOBS=0 turns it off; failures are ignored."""
+    import os
+    if os.environ.get("DSRG_B200_PIN_BLOBS", "1") == "0" or not isinstance(a, np.ndarray) or a.nbytes < (1 << 20):
+        return a
+    from dsrg_b200 import _lib
+    ptr = a.ctypes.data
+    if _PINNED_REGIONS.get(ptr) != a.nbytes:
+        L = _lib.lib()
+        if ptr in _PINNED_REGIONS:
+            L.dsrg_host_unregister(ptr)
+            del _PINNED_REGIONS[ptr]
+        while len(_PINNED_REGIONS) >= 16:      # blobs come and go in tests; a net has a handful
+            old = next(iter(_PINNED_REGIONS))
+            L.dsrg_host_unregister(old)
+            del _PINNED_REGIONS[old]
+        if L.dsrg_host_register(ptr, a.nbytes) == 0:
+            _PINNED_REGIONS[ptr] = a.nbytes
+    return a
+
+
+_IMAGE_BUFS = {}
+
+
+def _fingerprint(a):
+    """Cheap identity of a blob's current content: buffer address, shape and a strided sample of ~16 K values.
+    Used to recognise that DSRGLayer is fed the very blobs CRFLayer has just refined (train-s.prototxt:758-786)."""
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 16384)
+    return (a.ctypes.data, a.shape, str(a.dtype), hash(flat[::step].tobytes()))
+
+
+_LAST_CRF = {}   # what the engine's retained mean-field result was computed from
+
+
+def _share_crf():
+    import os
+    return os.environ.get("DSRG_B200_SHARE_CRF", "1") != "0"
+
+
 def _prepare_image(im, eng):
     """pylayers.py:70-75 / :315-319 (bilinear zoom to the map size, + mean pixel, np.round) and the
     ubyte cast of CRF.py:32, on the device: dsrg_prepare_image_host is byte-identical to the
     reference's scipy.ndimage.zoom(order=1) pipeline (tests/test_gpu_dropin.py)."""
-    return eng.prepare_image_host(_f32(im), (104.0, 117.0, 123.0))
+    key = (id(eng), im.shape[0])
+    if key not in _IMAGE_BUFS:   # pinned once per engine: the uint8 image comes back and goes in again with the pass
+        _IMAGE_BUFS[key] = _api.pinned_empty((im.shape[0], eng.H, eng.W, 3), np.uint8)
+    return eng.prepare_image_host(_f32(im), (104.0, 117.0, 123.0), out=_IMAGE_BUFS[key])
 
 
 def _clamped_writeback(blob_data, probs):
-    """The reference clamps the bottom blob in place (pylayers.py:67, :312); the device did the
-    clamp on its copy, so hand the values back to the blob."""
-    blob_data[...] = probs
+    """The reference clamps the bottom blob in place (pylayers.py:67, :312); the host entry point applied the
+    clamp to the array it was given -- which is the blob itself unless _f32 had to make a contiguous copy."""
+    if probs is not blob_data and not np.shares_memory(probs, blob_data):
+        blob_data[...] = probs
 
 
 class SoftmaxLayer(caffe.Layer):
@@ -94,6 +143,10 @@ class CRFLayer(caffe.Layer):
         eng.crflayer_forward_host(probs, im, _api.crf_params(12.0), log_out, self.result)  # scale_factor=12.0 (:82)
         _clamped_writeback(bottom[0].data, probs)
         top[0].data[...] = log_out
+        # the engine keeps the raw marginals: a DSRGLayer fed the same two blobs need not repeat the CRF
+        _LAST_CRF.clear()
+        _LAST_CRF.update(engine=eng, n=n, scale=12.0, probs=_fingerprint(bottom[0].data),
+                         image=_fingerprint(bottom[1].data))
 
     def backward(self, top, prop_down, bottom):
         grad = (1 - self.result) * top[0].diff[...]
@@ -192,27 +245,44 @@ class DSRGLayer(caffe.Layer):
             layer_params['iters'] = -1
         self._max_iters = layer_params['iters']
         self._iter_index = 0
+        # extension (not in the reference, whose refinement() hard-codes 12.0, pylayers.py:335): the CRF scale
+        self._scale_factor = float(layer_params.get('scale_factor', 12.0))
 
     def reshape(self, bottom, top):
         top[0].reshape(*bottom[1].data.shape)
 
     def forward(self, bottom, top):
         img_labels, probs, cues, im = bottom[0].data, bottom[1].data, bottom[2].data, bottom[3].data
-        seed_c = self.generate_seed(img_labels, probs, cues, im)
+        out = top[0].data
+        direct = isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
+        seed_c = self.generate_seed(img_labels, probs, cues, im, seeds_out=_pin(out) if direct else None)
         self._iter_index = self._iter_index + 1
-        top[0].data[...] = seed_c
+        if seed_c is not out:
+            top[0].data[...] = seed_c
 
     def backward(self, top, prop_down, bottom):
         bottom[1].diff[...] = top[0].diff
 
-    def generate_seed(self, labels, probs, cues, im):
+    def generate_seed(self, labels, probs, cues, im, seeds_out=None):
         """refinement (pylayers.py:310-331) + SRG over the batch (:333-344), fused on the device."""
         num, channels, height, width = probs.shape
-        p = _f32(probs)
         eng = _engine(num, channels, height, width)
-        image = _prepare_image(im, eng)
-        seeds = eng.dsrg_forward_host(_f32(labels).reshape(num, channels), p, _f32(cues), image,
-                                      _api.crf_params(12.0), self._th1, self._th2)
+        scale = getattr(self, "_scale_factor", 12.0)
+        if (_share_crf() and _LAST_CRF.get("engine") is eng and _LAST_CRF.get("n") == num and _LAST_CRF.get("scale") == scale
+                and _LAST_CRF.get("probs") == _fingerprint(probs) and _LAST_CRF.get("image") == _fingerprint(im)):
+            # same blobs as the CRFLayer that ran just before (already clamped in place by it): one refinement
+            # serves both layers; any other CRF call on this engine invalidates the retained result (DSRG_E_STATE)
+            try:
+                return eng.srg_last_crf_host(_f32(labels).reshape(num, channels), _pin(_f32(cues)), self._th1, self._th2,
+                                             seeds_out=seeds_out)
+            except _api.DsrgError:
+                pass
+        _LAST_CRF.clear()
+        p = _pin(_f32(probs))
+        image = _prepare_image(_pin(_f32(im)), eng)
+        seeds = eng.dsrg_forward_host(_f32(labels).reshape(num, channels), p, _pin(_f32(cues)), image,
+                                      _api.crf_params(getattr(self, "_scale_factor", 12.0)), self._th1, self._th2,
+                                      seeds_out=seeds_out)
         _clamped_writeback(probs, p)
         return seeds
 

@@ -65,6 +65,23 @@ def make_image(rng, H, W, variant="smooth"):
         return np.round((im - lo) / (hi - lo) * 255.0).astype(np.uint8)
     if variant == "noise":
         return rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    if variant == "photo":
+        # natural-image statistics: amplitude spectrum ~ 1/f (power 1/f^2), a shared luminance field plus weaker
+        # independent chroma fields, stretched to the full 8-bit range with a few percent clipped like a photo
+        fy, fx = np.fft.fftfreq(H)[:, None], np.fft.fftfreq(W)[None, :]
+        f = np.sqrt(fy * fy + fx * fx)
+        f[0, 0] = 1.0
+        amp = 1.0 / f
+        amp[0, 0] = 0.0
+
+        def field():
+            ph = np.exp(2j * np.pi * rng.rand(H, W))
+            x = np.real(np.fft.ifft2(amp * ph))
+            return x / x.std()
+        lum = field()
+        im = np.stack([lum + 0.35 * field() for _ in range(3)], axis=-1)
+        lo, hi = np.percentile(im, 1.0), np.percentile(im, 99.0)
+        return np.round(np.clip((im - lo) / (hi - lo), 0.0, 1.0) * 255.0).astype(np.uint8)
     raise ValueError(variant)
 
 

@@ -47,6 +47,10 @@ int dsrg_current_device(void);
 /* Pinned host memory so the *_host entry points overlap their copies (cudaHostAlloc). */
 void *dsrg_host_alloc(size_t bytes);
 void dsrg_host_free(void *p);
+/* Page-lock memory the caller already owns (a Caffe blob's CPU buffer in CPU mode, a numpy array) so that the
+ * *_host entry points copy from / to it asynchronously at full PCIe rate (cudaHostRegister / Unregister). */
+int dsrg_host_register(void *p, size_t bytes);
+int dsrg_host_unregister(void *p);
 
 /* ------------------------------------------------------------------------------------------
  * Pairwise parameters of krahenbuhl2013.CRF -- CRF/krahenbuhl2013/CRF.py:31-32 passes
@@ -265,6 +269,20 @@ int dsrg_crflayer_forward_dev(dsrg_engine *e, int B, float *probs_dev, const uin
 int dsrg_crflayer_forward_host(dsrg_engine *e, int B, float *probs_host, const uint8_t *image_host,
                                const dsrg_crf_params *params, float *log_out_host,
                                float *result_host);
+
+/*
+ * One refinement, two consumers.  In the reference's net CRFLayer and DSRGLayer are fed the same two blobs
+ * (train-s.prototxt:758-786) and each runs the whole dense CRF on them (pylayers.py:82 and :326).  The raw
+ * marginals of an engine's last mean-field pass stay on the device; these entry points let a second consumer
+ * use them instead of repeating the pass:
+ *   dsrg_srg_last_crf_host       : generate_seed_step over the batch on those marginals (float64 clamp +
+ *                                  renormalisation fused in, exactly what dsrg_dsrg_forward_* does after its CRF)
+ *   dsrg_crf_last_marginals_host : the raw float32 marginals themselves
+ * Both return DSRG_E_STATE unless the engine's last pass was a CRF over exactly B images.
+ */
+int dsrg_srg_last_crf_host(dsrg_engine *e, int B, const float *labels_host, const float *cues_host, double th1,
+                           double th2, float *seeds_out_host);
+int dsrg_crf_last_marginals_host(dsrg_engine *e, int B, float *out_host, int out_layout);
 
 /*
  * BalancedSeedLossLayer (pylayers.py:120-152).  Forward writes the LOCAL sums

@@ -132,3 +132,92 @@ def test_softmax_and_constrain_loss_layers(torch_cuda):
     safe = (np.abs(ratio - 0.05) > 1e-5) & (np.abs(ratio - 20) > 1e-3)
     np.testing.assert_allclose(bottom[0].diff[safe], gp[safe], rtol=2e-4, atol=1e-9)
     np.testing.assert_allclose(bottom[1].diff[safe], gl[safe], rtol=2e-4, atol=1e-9)
+
+
+def test_crf_and_dsrg_layers_share_one_refinement(torch_cuda, monkeypatch):
+    """train-s.prototxt:758-786 feeds CRFLayer and DSRGLayer the same two blobs and the reference refines them
+    twice (pylayers.py:82, :326).  The drop-in keeps the CRFLayer's marginals on the device and DSRGLayer grows
+    its seeds from them: no second mean-field loop, and the seeds are exactly the reference SRG applied to the
+    float64 renormalisation of those very marginals."""
+    labels, probs, cues, images = training_blobs(n=3, start=910)
+    n = probs.shape[0]
+    crf, b_crf, t_crf = fake_caffe.run_layer(pylayers.CRFLayer, [probs, images])
+    from pylayers import pylayers as _pl
+    eng = _pl._engine(*probs.shape)
+    raw = eng.crf_last_marginals_host(n)                       # what the engine retained
+    r64 = crf_oracle.renormalise(raw)
+    np.testing.assert_allclose(np.exp(t_crf[0].data), r64, rtol=2e-6, atol=1e-9)   # CRFLayer's top is log of the same
+    eng.take_launch_count()
+    # DSRGLayer on the SAME blob objects (Caffe hands both layers views of the same memory)
+    dsrg = pylayers.DSRGLayer()
+    dsrg.param_str = "{'th1': 0.99, 'th2': 0.85}"
+    bottom = [fake_caffe.Blob(labels), b_crf[0], fake_caffe.Blob(cues), b_crf[1]]
+    top = [fake_caffe.Blob()]
+    dsrg.setup(bottom, top)
+    dsrg.reshape(bottom, top)
+    dsrg.forward(bottom, top)
+    launches = eng.take_launch_count()
+    assert 0 < launches <= 8, launches                         # SRG only: no lattice build, no tile / blur kernels
+    for b in range(n):
+        want = srg_oracle.srg_closed_form(labels[b, 0, 0], cues[b], r64[b], 0.99, 0.85)
+        assert np.array_equal(top[0].data[b], want)
+    shared = top[0].data.copy()
+    # without sharing the layer refines again: same seeds up to threshold ties under the atomics' noise
+    monkeypatch.setenv("DSRG_B200_SHARE_CRF", "0")
+    dsrg.forward(bottom, top)
+    assert eng.take_launch_count() > 40
+    assert int((top[0].data != shared).sum()) <= 4
+    monkeypatch.delenv("DSRG_B200_SHARE_CRF")
+    # other blobs in between invalidate the retained result: DSRGLayer falls back to its own refinement
+    fake_caffe.run_layer(pylayers.CRFLayer, [probs, images])
+    other = probs.copy()
+    other[:, :, 10:20, 10:20] = other[:, :, 10:20, 10:20][:, ::-1].copy()
+    bottom2 = [fake_caffe.Blob(labels), fake_caffe.Blob(other), fake_caffe.Blob(cues), b_crf[1]]
+    eng.take_launch_count()
+    dsrg.forward(bottom2, top)
+    assert eng.take_launch_count() > 40
+
+
+@pytest.mark.parametrize("H,W,sf,nimg", [(41, 41, 12.0, 6), (321, 321, 1.0, 2), (513, 513, 1.0, 1)])
+def test_crf_to_srg_seam_is_quantified(torch_cuda, H, W, sf, nimg, capsys):
+    """How far the fused GPU pass can drift from the reference's CPU pipeline: its CRF marginals differ from the
+    oracle's by <= 1e-4, so a label-map pixel may flip only where the deciding value sits that close to a threshold
+    (0.85 / 0.99, pylayers.py:251-257) or to the runner-up class.  Every flipped label-map pixel must be explained
+    that way; the resulting seed differences (a flip can flood a component) are counted and printed."""
+    from dsrg_b200 import api
+    torch = torch_cuda
+    batch = synth.make_batch(nimg, H, W, cues="cam", image="smooth", start=700)
+    eng = api.Engine(nimg, H, W, 21)
+    params = api.crf_params(sf)
+    d_p = torch.from_numpy(batch["probs"]).cuda()
+    d_seeds, d_q = torch.empty_like(d_p), torch.empty_like(d_p)
+    eng.dsrg_forward_dev(torch.from_numpy(batch["labels"]).cuda(), d_p, torch.from_numpy(batch["cues"]).cuda(),
+                         torch.from_numpy(batch["image"]).cuda(), params, 0.99, 0.85, d_seeds, crf_out=d_q)
+    torch.cuda.synchronize()
+    seeds, q = d_seeds.cpu().numpy(), d_q.cpu().numpy()
+    clamped = batch["probs"].copy()
+    clamped[clamped < 1e-4] = 1e-4
+    flips = seed_diff = unexplained = 0
+    worst = 0.0
+    for b in range(nimg):
+        ref_q = np.transpose(crf_oracle.CRF(batch["image"][b], np.ascontiguousarray(np.transpose(clamped[b], (1, 2, 0))), 10, sf), (2, 0, 1))
+        assert np.abs(ref_q - q[b]).max() <= 1e-4
+        r_ref, r_gpu = crf_oracle.renormalise(ref_q), crf_oracle.renormalise(q[b])
+        lm_ref = srg_oracle.label_map_closed_form(batch["labels"][b], batch["cues"][b], r_ref, 0.99, 0.85)
+        lm_gpu = srg_oracle.label_map_closed_form(batch["labels"][b], batch["cues"][b], r_gpu, 0.99, 0.85)
+        want = srg_oracle.srg_closed_form(batch["labels"][b], batch["cues"][b], r_ref, 0.99, 0.85)
+        seed_diff += int((want != seeds[b]).sum())
+        ys, xs = np.nonzero(lm_ref != lm_gpu)
+        present = np.where(batch["labels"][b] == 1)[0]
+        for y, x in zip(ys, xs):
+            flips += 1
+            v = np.sort(r_ref[present, y, x])[::-1]
+            margin = min(abs(v[0] - 0.85), abs(v[0] - 0.99), (v[0] - v[1]) if len(v) > 1 else 1.0)
+            worst = max(worst, margin)
+            if margin > 2e-4:    # two marginals, each within 1e-4 of the oracle
+                unexplained += 1
+    with capsys.disabled():
+        print("\n[seam %dx%d sf=%g, %d images] label-map flips: %d (max distance to a decision boundary %.2e), "
+              "seed values differing from the CPU pipeline: %d of %d" % (H, W, sf, nimg, flips, worst, seed_diff, seeds.size))
+    assert unexplained == 0
+    eng.close()
