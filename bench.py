@@ -8,6 +8,9 @@ One "step" = one pass of the hot path over one batch of synthetic images:
                      seeded region growing (th 0.99/0.85), batch 64 @ 321x321x21
   crf321 / srg321  : the CRF-only / SRG-only configurations of BASELINE.json (batch 64)
   full513          : the same full pass + balanced seeding loss, batch 16 @ 513x513x21
+  sweep4096        : BASELINE config 5 -- 4096 images @ 321x321x21, image i on rank floor(i*R/4096)
+                     (dsrg_b200/shard.py), each rank works through its shard in batches of 64: STRONG scaling.
+                     The default (dsrg321) line also carries a `sweep4096` object measured in the same run.
 
 `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line (rank 0).  Under torchrun
 (WORLD_SIZE > 1) every rank runs the same per-rank batch on its own GPU (images shard with no
@@ -37,7 +40,9 @@ WORKLOADS = {
     "crf321": (321, 321, 64, "crf"),
     "srg321": (321, 321, 64, "srg"),
     "full513": (513, 513, 16, "crf+srg+loss"),
+    "sweep4096": (321, 321, 64, "crf+srg"),   # 4096 images in all, sharded; 64 = the batch a rank processes at a time
 }
+SWEEP_IMAGES = 4096
 M = 21
 T_ITERS = 10
 TH1, TH2 = 0.99, 0.85
@@ -51,8 +56,15 @@ def algorithmic_bytes_per_image(what, N):
     return {"crf": b_crf, "srg": b_srg, "crf+srg": b_crf + b_srg, "crf+srg+loss": b_crf + b_srg + b_loss}[what]
 
 
+def kernel_survey_bytes(tag, N, B):
+    """SURVEY.md 8(d) bytes ONE launch accounts for: the CRF budget is N(3 + 8M + 12MT), i.e. 12*M*N per image and
+    mean-field iteration (read U, read Q, write Q), and one tile-kernel launch is one iteration."""
+    per = {"mf_tile": 12 * M * N, "srg_label": 8 * M * N, "srg_emit": 4 * M * N, "mf_init": 12 * M * N, "mf_export": 8 * M * N}
+    return per.get(tag, 0) * B
+
+
 def kernel_algorithmic_bytes(tag, N, B):
-    """Algorithmic bytes ONE launch of a kernel class moves for a batch of B images."""
+    """Bytes ONE launch of a kernel class must move given OUR design, for a batch of B images."""
     per = {
         "mf_tile": 4 * M * N,           # the fused slice+update+splat kernel streams U once; Q stays on chip
         "mf_init": 8 * M * N + 4 * M * N,
@@ -273,17 +285,32 @@ def run_b200(args, rank, local_rank, world):
     d_q = torch.empty_like(d_unary) if what == "crf" else None
     d_terms = torch.zeros(2, device=dev)
 
-    def step():
+    from dsrg_b200 import shard
+
+    def shard_sizes():
+        """BASELINE config 5: this rank's contiguous share of the 4096-image job, in batches of at most B."""
+        lo, hi = shard.shard_range(SWEEP_IMAGES, rank, world)
+        return [min(B, hi - b) for b in range(lo, hi, B)]
+
+    sweep = args.workload == "sweep4096"
+    sizes = shard_sizes() if sweep else [B]
+    images_per_step = SWEEP_IMAGES if sweep else world * B      # whole job, all ranks
+
+    def one(nb):
         if what == "crf":
-            eng.crf_dev(d_unary, d_image, params, d_q)
+            eng.crf_dev(d_unary[:nb], d_image[:nb], params, d_q[:nb])
         elif what == "srg":
-            eng.srg_dev(d_labels, d_probs, d_cues, TH1, TH2, d_seeds)
+            eng.srg_dev(d_labels[:nb], d_probs[:nb], d_cues[:nb], TH1, TH2, d_seeds[:nb])
         else:
-            eng.dsrg_forward_dev(d_labels, d_probs, d_cues, d_image, params, TH1, TH2, d_seeds)
+            eng.dsrg_forward_dev(d_labels[:nb], d_probs[:nb], d_cues[:nb], d_image[:nb], params, TH1, TH2, d_seeds[:nb])
             if "loss" in what:
-                eng.seedloss_forward_dev(d_probs, d_seeds, d_terms)
+                eng.seedloss_forward_dev(d_probs[:nb], d_seeds[:nb], d_terms)
                 if dist is not None:
                     dist.all_reduce(d_terms)   # the path's only collective: 2 floats
+
+    def step():
+        for nb in sizes:
+            one(nb)
 
     # a real stream (not the legacy default stream): repeated passes are then replayed as CUDA graphs
     side = torch.cuda.Stream(device=dev)
@@ -325,7 +352,7 @@ def run_b200(args, rank, local_rank, world):
     ms = timed(step, args.steps)
     clocks = sampler.stop() if sampler else None
     launches = eng.take_launch_count()
-    value = world * B * args.steps / (ms * 1e-3)
+    value = images_per_step * args.steps / (ms * 1e-3)
 
     # per-kernel durations by CUDA events on the launching stream, same K steps repeated
     eng.profile(True)
@@ -341,8 +368,9 @@ def run_b200(args, rank, local_rank, world):
     if top:
         tag, (tms, cnt) = top
         per_launch_s = tms * 1e-3 / cnt
-        ab = kernel_algorithmic_bytes(tag, N, B)
-        ach = ab / per_launch_s / 1e9 if ab else 0.0
+        sb = kernel_survey_bytes(tag, N, B)          # what `achieved` / `frac` are computed on
+        ab = kernel_algorithmic_bytes(tag, N, B)     # what this design has to move (U once; Q stays on chip)
+        ach = sb / per_launch_s / 1e9 if sb else 0.0
         traffic = None   # dram__bytes_read+write per launch from the last committed ncu --set full capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(tag)
@@ -351,7 +379,12 @@ def run_b200(args, rank, local_rank, world):
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": tag, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "bytes_basis": "SURVEY.md 8(d): 12*M*N per image and mean-field iteration for the tile kernel",
+                    "survey_bytes_per_launch": sb, "algorithmic_bytes_per_launch": ab,
+                    "frac_own_bytes": (ab / per_launch_s / 1e9 / peak) if ab else None,
+                    "traffic_over_survey_bytes": (traffic / sb) if (traffic and sb) else None,
+                    "traffic_over_own_bytes": (traffic / ab) if (traffic and ab) else None,
                     "avg_launch_ms": per_launch_s * 1e3, "share_of_step": tms / total_kernel_ms,
                     "step_algorithmic_GBs": algorithmic_bytes_per_image(what, N) * B * args.steps / (ms * 1e-3) / 1e9,
                     "step_frac": algorithmic_bytes_per_image(what, N) * B * args.steps / (ms * 1e-3) / 1e9 / peak,
@@ -369,19 +402,26 @@ def run_b200(args, rank, local_rank, world):
             h_unary = api.pinned_empty((B, H, W, M), np.float32); h_unary[...] = np.transpose(batch["probs"], (0, 2, 3, 1))
             h_q = api.pinned_empty((B, H, W, M), np.float32)
 
-            def host_step():
-                eng.crf_host(h_unary, h_image, params, out=h_q)
+            def host_one(nb):
+                eng.crf_host(h_unary[:nb], h_image[:nb], params, out=h_q[:nb])
             h2d, d2h = h_unary.nbytes + h_image.nbytes, h_q.nbytes
         elif what == "srg":
-            def host_step():
-                eng.srg_host(h_labels, h_probs, h_cues, TH1, TH2, seeds_out=h_seeds)
+            def host_one(nb):
+                eng.srg_host(h_labels[:nb], h_probs[:nb], h_cues[:nb], TH1, TH2, seeds_out=h_seeds[:nb])
             h2d, d2h = h_labels.nbytes + h_probs.nbytes + h_cues.nbytes, h_seeds.nbytes
         else:
-            def host_step():
-                eng.dsrg_forward_host(h_labels, h_probs, h_cues, h_image, params, TH1, TH2, seeds_out=h_seeds)
+            def host_one(nb):
+                eng.dsrg_forward_host(h_labels[:nb], h_probs[:nb], h_cues[:nb], h_image[:nb], params, TH1, TH2,
+                                      seeds_out=h_seeds[:nb])
             h2d = h_labels.nbytes + h_probs.nbytes + h_cues.nbytes + h_image.nbytes
-            d2h = h_seeds.nbytes + h_probs.nbytes   # seeds + the in-place-clamped probs blob
-        for _ in range(2):
+            d2h = h_seeds.nbytes + h_probs.nbytes   # seeds + the in-place-clamped probs blob (travels as a bit mask)
+        per_image_h2d, per_image_d2h = h2d / B, d2h / B
+
+        def host_step():
+            for nb in sizes:
+                host_one(nb)
+        h2d, d2h = per_image_h2d * sum(sizes), per_image_d2h * sum(sizes)
+        for _ in range(1 if sweep else 2):
             host_step()
         barrier()
         t0 = time.perf_counter()
@@ -393,10 +433,91 @@ def run_b200(args, rank, local_rank, world):
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": world * B * args.steps / dt, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+        e2e = {"value": images_per_step * args.steps / dt, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "api": "dsrg_*_host (C ABI, pinned host buffers)",
                "note": "inputs are re-sent from the same pinned buffers every step; the in-place 1e-4 clamp of probs "
                        "(pylayers.py:312) therefore only changes values during the first warm-up step"}
+
+    extras = {}
+    if args.workload == "dsrg321" and not args.no_extras and not args.no_e2e:
+        # --- BASELINE config 5 in the same run: the 4096-image job sharded over the ranks (strong scaling) ---
+        sw_sizes = shard_sizes()
+
+        def sweep_dev():
+            with torch.cuda.stream(side):
+                for nb in sw_sizes:
+                    one(nb)
+        sw_ms = timed(sweep_dev, 1)
+        barrier()
+        t0 = time.perf_counter()
+        for nb in sw_sizes:
+            host_one(nb)
+        torch.cuda.synchronize()
+        sw_dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([sw_dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sw_dt = float(t.item())
+        extras["sweep4096"] = {"what": "BASELINE config 5: %d images @ 321x321x21, contiguous shards (dsrg_b200/shard.py), "
+                                       "batches of %d per rank" % (SWEEP_IMAGES, B),
+                               "scaling": "strong", "images": SWEEP_IMAGES, "images_this_rank": int(sum(sw_sizes)),
+                               "value": SWEEP_IMAGES / (sw_ms * 1e-3), "unit": "images/s", "ms": sw_ms,
+                               "e2e": {"value": SWEEP_IMAGES / sw_dt, "unit": "images/s"}}
+    if args.workload in ("dsrg321", "train41") and rank == 0 and world == 1 and not args.no_extras and not args.no_e2e:
+        # --- through the plugin call itself: pylayers.DSRGLayer.forward on Caffe-style host blobs ---
+        from dsrg_b200.dropin import caffe_shim
+        caffe_shim.install()
+        import pylayers
+        sf = 12.0 if args.workload == "train41" else 1.0
+        Hi = 321                                     # the net's input images are 321x321 whatever the map size
+        if H == Hi:
+            img = batch["image"]
+        else:
+            from dsrg_b200 import synth
+            uniq = [synth.make_image(np.random.RandomState(50 + i), Hi, Hi, IMAGE_VARIANT) for i in range(min(B, 8))]
+            img = np.stack([uniq[i % len(uniq)] for i in range(B)])
+        net_images = np.ascontiguousarray(np.transpose(img.astype(np.float32) - np.array([104.0, 117.0, 123.0], np.float32),
+                                                       (0, 3, 1, 2)))
+        layer = pylayers.DSRGLayer()
+        layer.param_str = "{'th1': %g, 'th2': %g, 'scale_factor': %g}" % (TH1, TH2, sf)
+        bottom = [caffe_shim.Blob(batch["labels"].reshape(B, 1, 1, M)), caffe_shim.Blob(batch["probs"]),
+                  caffe_shim.Blob(batch["cues"]), caffe_shim.Blob(net_images)]
+        top = [caffe_shim.Blob()]
+        layer.setup(bottom, top)
+        layer.reshape(bottom, top)
+        for _ in range(2):
+            layer.forward(bottom, top)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            layer.forward(bottom, top)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        extras["e2e_layer"] = {"value": B * args.steps / dt, "unit": "images/s", "ms_per_step": 1e3 * dt / args.steps,
+                               "api": "pylayers.DSRGLayer.forward (drop-in Python layer) on pageable numpy blobs of a "
+                                      "pycaffe stand-in; the layer page-locks them on first use (cudaHostRegister), "
+                                      "the float32 net images (B,3,%d,%d) are zoomed / mean-shifted / rounded on the "
+                                      "device every step" % (Hi, Hi),
+                               "h2d_bytes_per_step": int(sum(b.data.nbytes for b in bottom)),
+                               "d2h_bytes_per_step": int(top[0].data.nbytes + bottom[1].data.nbytes)}
+    if args.workload == "dsrg321" and not args.no_extras and not sweep:
+        # --- the other image statistics: a 1/f "photo-like" spectrum and uniform noise (worst case) ---
+        variants = {IMAGE_VARIANT: {"value": value, "ms_per_step": ms / args.steps}}
+        for var in ("smooth", "photo", "noise"):
+            if var in variants:
+                continue
+            from dsrg_b200 import synth
+            uniq = [synth.make_image(np.random.RandomState(1234 + i), H, W, var) for i in range(min(B, 8))]
+            imgs = np.stack([uniq[i % len(uniq)] for i in range(B)])
+            d_image.copy_(torch.from_numpy(imgs).to(dev))
+            for _ in range(3):
+                step()
+            vms = timed(step, 3)
+            variants[var] = {"value": world * B * 3 / (vms * 1e-3), "ms_per_step": vms / 3}
+        d_image.copy_(torch.from_numpy(batch["image"]).to(dev))
+        extras["image_variants"] = {"unit": "images/s", "what": "device-resident, same probs / cues, image statistics varied: "
+                                    "smooth = Gaussian-filtered noise, photo = 1/f amplitude spectrum, noise = uniform",
+                                    "values": variants}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -411,14 +532,15 @@ def run_b200(args, rank, local_rank, world):
         emit(json.dumps({
             "metric": "images/s, SRG + DenseCRF pass at %dx%dx%d" % (H, W, M), "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if sweep else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
             "config": {"workload": args.workload, "what": what, "H": H, "W": W, "labels": M, "batch_per_gpu": B,
-                       "global_batch": B * world, "mean_field_iters": T_ITERS, "sigma": "bilateral 80/13, spatial 3, scale_factor %g" % (12.0 if args.workload == "train41" else 1.0),
+                       "global_batch": SWEEP_IMAGES if sweep else B * world, "mean_field_iters": T_ITERS, "sigma": "bilateral 80/13, spatial 3, scale_factor %g" % (12.0 if args.workload == "train41" else 1.0),
                        "thresholds": [TH1, TH2], "images": "%s, cam-like cues, 8 distinct images repeated" % IMAGE_VARIANT,
                        "l2": "inputs larger than L2 (%.0f MB of probs+cues per step)" % (2 * 4 * M * N * B / 1e6),
                        "parallelism": "dp%d (images shard, no data-path collective)" % world},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "kernels": kernels, "cpu_baseline": cpu_baseline, **extras,
         }))
     eng.close()
     if dist is not None:
@@ -455,9 +577,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning aid: skip the host-buffer leg (the line is then not a valid result)")
-    ap.add_argument("--images", default="smooth", choices=["smooth", "noise"],
-                    help="synthetic image variant: smooth (headline) or uniform noise (worst case: every tile "
-                         "overflows the shared-memory path)")
+    ap.add_argument("--no-extras", action="store_true", help="skip sweep4096 / e2e_layer / image_variants of the default line")
+    ap.add_argument("--images", default="smooth", choices=["smooth", "photo", "noise"],
+                    help="synthetic image variant: smooth (headline), photo (1/f spectrum) or uniform noise (worst "
+                         "case: every tile overflows the shared-memory path)")
     args = ap.parse_args()
     global IMAGE_VARIANT
     IMAGE_VARIANT = args.images

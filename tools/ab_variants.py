@@ -44,7 +44,7 @@ def do_run(names, rounds, extra):
             env.pop("DSRG_B200_LIB", None)
             if n != "base":
                 env["DSRG_B200_LIB"] = lib_path(n)
-            p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--no-e2e"] + extra,
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--no-e2e", "--no-extras"] + extra,
                                env=env, capture_output=True, text=True)
             line = [l for l in p.stdout.splitlines() if l.startswith("{")]
             if p.returncode != 0 or not line:
