@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdsrg_b200.so")
-SOURCES = ["api.cu", "graph.cu", "lattice.cu", "tiles.cu", "meanfield.cu", "srg.cu", "loss.cu", "wire.cu", "numa.cu", "prep.cu", "post.cu", "annot.cu"]
+SOURCES = ["api.cu", "graph.cu", "lattice.cu", "tiles.cu", "meanfield.cu", "meanfield_wide.cu", "srg.cu", "loss.cu", "wire.cu", "numa.cu", "prep.cu", "post.cu", "annot.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp", "--fmad=true"]
 

@@ -322,10 +322,10 @@ void dsrg_crf_params_default(dsrg_crf_params *p, float scale_factor, float color
 }
 
 dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) {
-    if (max_batch < 1 || H < 1 || W < 1 || M < 1 || M > DSRG_MAX_LABELS ||
+    if (max_batch < 1 || H < 1 || W < 1 || M < 1 || M > DSRG_MAX_LABELS_WIDE ||
         (long long)H * W > (1ll << 24)) {
         set_error("bad engine shape (max_batch=%d H=%d W=%d M=%d; M <= %d)", max_batch, H, W, M,
-                  DSRG_MAX_LABELS);
+                  DSRG_MAX_LABELS_WIDE);
         return nullptr;
     }
     int ndev = 0;
@@ -883,8 +883,8 @@ void dsrg_densecrf_release_engines(void) {
 }
 
 dsrg_densecrf *dsrg_densecrf_create(int W, int H, int nlabels) {
-    if (W < 1 || H < 1 || nlabels < 1 || nlabels > DSRG_MAX_LABELS || (long long)H * W > (1ll << 24)) {
-        set_error("bad shape (W=%d H=%d nlabels=%d; nlabels <= %d)", W, H, nlabels, DSRG_MAX_LABELS);
+    if (W < 1 || H < 1 || nlabels < 1 || nlabels > DSRG_MAX_LABELS_WIDE || (long long)H * W > (1ll << 24)) {
+        set_error("bad shape (W=%d H=%d nlabels=%d; nlabels <= %d)", W, H, nlabels, DSRG_MAX_LABELS_WIDE);
         return nullptr;
     }
     if (dsrg_device_count() < 1) {

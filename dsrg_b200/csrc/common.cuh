@@ -103,6 +103,10 @@ int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s);
 // ---- meanfield.cu ----
 int meanfield_run(Engine *e, int B, const float *unary, int unary_layout, bool clamp_inplace,
                   float *unary_rw, const dsrg_crf_params &p, cudaStream_t s);
+// ---- meanfield_wide.cu: label counts above DSRG_MAX_LABELS ----
+int meanfield_run_wide(Engine *e, int B, const float *unary, int unary_layout, bool clamp_inplace,
+                       float *unary_rw, const dsrg_crf_params &p, cudaStream_t s);
+int wide_weights(Engine *e, Lattice &L, int nb, cudaStream_t s);
 int meanfield_export(Engine *e, int B, float *out, int layout, cudaStream_t s);
 int meanfield_export_map(Engine *e, int B, int32_t *labels, cudaStream_t s);
 int meanfield_export_renorm(Engine *e, int B, float *result_out, float *log_out, cudaStream_t s);

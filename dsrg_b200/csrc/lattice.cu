@@ -397,7 +397,8 @@ int lattice_build(Engine *e, Lattice &L, int B, const uint8_t *image_dev, cudaSt
     const float alpha = 1.0f / (1 + powf(2, -L.d));  // permutohedral.cpp:510
     DSRG_LAUNCH(e, T_LAT_NORM, s, k_norm_slice<<<gp, kThreads, 0, s>>>(L.off, L.bary, L.rowbase, src, L.norm, L.N, dp1, alpha));
     DSRG_CUDA_TRY(cudaGetLastError());
-    return tiles_build(e, L, nb, s);
+    // the tile-local views serve the fused kernel (up to DSRG_MAX_LABELS labels); the wide path only needs bary * norm
+    return e->MP > DSRG_MAX_LABELS ? wide_weights(e, L, nb, s) : tiles_build(e, L, nb, s);
 }
 
 }  // namespace dsrg

@@ -238,7 +238,14 @@ k_constrain_bwd(const float *probs, const float *logs, float *gp, float *gl, lon
     }
 }
 
+static int narrow_only(const Engine *e, const char *what) {
+    if (e->M <= DSRG_MAX_LABELS) return DSRG_OK;
+    set_error("%s supports at most %d labels (engine has %d)", what, DSRG_MAX_LABELS, e->M);
+    return DSRG_E_INVALID;
+}
+
 int softmax_forward(Engine *e, int B, const float *x, float *probs, cudaStream_t s) {
+    if (int rc = narrow_only(e, "SoftmaxLayer")) return rc;
     dim3 g(cdiv(e->N, kThreads), B);
     DSRG_LAUNCH(e, T_LOSS, s, k_softmax_fwd<DSRG_MAX_LABELS><<<g, kThreads, 0, s>>>(x, probs, e->M, e->N));
     DSRG_CUDA_TRY(cudaGetLastError());
@@ -246,6 +253,7 @@ int softmax_forward(Engine *e, int B, const float *x, float *probs, cudaStream_t
 }
 
 int softmax_backward(Engine *e, int B, const float *x, const float *top, float *grad, cudaStream_t s) {
+    if (int rc = narrow_only(e, "SoftmaxLayer")) return rc;
     dim3 g(cdiv(e->N, kThreads), B);
     DSRG_LAUNCH(e, T_LOSS, s, k_softmax_bwd<DSRG_MAX_LABELS><<<g, kThreads, 0, s>>>(x, top, grad, e->M, e->N));
     DSRG_CUDA_TRY(cudaGetLastError());

@@ -743,6 +743,7 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
 
 int meanfield_run(Engine *e, int B, const float *unary, int unary_layout, bool clamp_inplace,
                   float *unary_rw, const dsrg_crf_params &p, cudaStream_t s) {
+    if (e->MP > DSRG_MAX_LABELS) return meanfield_run_wide(e, B, unary, unary_layout, clamp_inplace, unary_rw, p, s);
     switch (e->MP) {
         case 4: return run_impl<4>(e, B, unary, unary_layout, clamp_inplace, unary_rw, p, s);
         case 8: return run_impl<8>(e, B, unary, unary_layout, clamp_inplace, unary_rw, p, s);

@@ -127,6 +127,10 @@ static int predict_mask(Engine *e, int mode, int n_scales, const float *const *s
         set_error("bad mode %d", mode);
         return DSRG_E_INVALID;
     }
+    if (e->M > DSRG_MAX_LABELS) {
+        set_error("predict_mask post-processing supports at most %d labels (engine has %d)", DSRG_MAX_LABELS, e->M);
+        return DSRG_E_INVALID;
+    }
     if (n_scales < 1 || (mode == DSRG_POST_ZOOM_PROBS && n_scales != 1) || !scores || !hs || !ws || !result ||
         (smooth && (!image || !p)) || n_sel < 0 || n_sel > DSRG_MAX_LABELS || (n_sel > 0 && !labels_sel)) {
         set_error("bad argument");

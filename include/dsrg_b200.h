@@ -33,7 +33,12 @@ extern "C" {
 #define DSRG_LAYOUT_NHWC 0
 #define DSRG_LAYOUT_NCHW 1
 
-#define DSRG_MAX_LABELS 32 /* labels per pixel supported by the register-tiled kernels */
+#define DSRG_MAX_LABELS 32 /* labels per pixel of the fused, register-tiled kernels (the 21-class hot path) */
+/* CRF (batch, layer and DenseCRF-object entry points) and SRG accept up to this many labels: above DSRG_MAX_LABELS
+ * the mean field runs on a generic label-chunked path (csrc/meanfield_wide.cu) -- the reference's COCO tool uses
+ * DenseCRF(W, H, 81), training/tools/test-coco.py.  The Softmax / ConstrainLoss layers and the predict_mask
+ * post-processing are built for at most DSRG_MAX_LABELS. */
+#define DSRG_MAX_LABELS_WIDE 255
 
 int dsrg_version(void);               /* 10000*major + 100*minor + patch */
 const char *dsrg_last_error(void);    /* message of the last failing call on this thread */

@@ -152,7 +152,54 @@ def test_crf_and_srg_other_label_counts(torch_cuda, M):
 
 def test_label_count_limit_is_reported(torch_cuda):
     with pytest.raises(api.DsrgError):
-        api.Engine(1, 8, 8, 33)
+        api.Engine(1, 8, 8, 256)
+    eng = api.Engine(1, 8, 8, 33)       # wide path: CRF and SRG only
+    with pytest.raises(api.DsrgError):
+        eng.softmax_forward_host(np.zeros((1, 33, 8, 8), np.float32))
+    eng.close()
+
+
+@pytest.mark.parametrize("M,H,W,sf,img", [(33, 23, 31, 1.0, "smooth"), (81, 37, 45, 1.0, "smooth"), (81, 30, 26, 12.0, "noise")])
+def test_crf_and_srg_wide_label_counts(torch_cuda, M, H, W, sf, img):
+    """Label counts above 32 (the reference's COCO tool: DenseCRF(W, H, 81), training/tools/test-coco.py) run on the
+    generic label-chunked path (csrc/meanfield_wide.cu): batch entry point in both layouts, the DenseCRF object,
+    map(), and the SRG with the same label count -- against the oracles."""
+    from oracle import srg_oracle
+    torch = torch_cuda
+    B = 2
+    rng = np.random.RandomState(M + H)
+    logits = rng.randn(B, H, W, M).astype(np.float32) * 2
+    logits[:, H // 4: H // 2, W // 3:, 5] += 4
+    pr = np.exp(logits - logits.max(-1, keepdims=True))
+    pr /= pr.sum(-1, keepdims=True)
+    unary = np.log(np.maximum(pr, 1e-5)).astype(np.float32)
+    image = np.stack([synth.make_image(np.random.RandomState(9 + b), H, W, img) for b in range(B)])
+    want = np.stack([crf_oracle.CRF(image[b], unary[b], 10, sf) for b in range(B)])
+    eng = api.Engine(B, H, W, M)
+    d_un = torch.from_numpy(unary).cuda()
+    d_out = torch.empty_like(d_un)
+    eng.crf_dev(d_un, torch.from_numpy(image).cuda(), api.crf_params(sf), d_out)
+    assert np.abs(d_out.cpu().numpy() - want).max() <= TOL
+    d_nchw = d_un.permute(0, 3, 1, 2).contiguous()
+    d_out2 = torch.empty_like(d_nchw)
+    eng.crf_dev(d_nchw, torch.from_numpy(image).cuda(), api.crf_params(sf), d_out2, unary_layout=1, out_layout=1)
+    assert np.abs(d_out2.permute(0, 2, 3, 1).cpu().numpy() - want).max() <= TOL
+    c = api.DenseCRF(W, H, M)
+    c.set_unary_energy(-unary[0].ravel())
+    c.add_pairwise_energy(10, 80 / sf, 80 / sf, 13, 13, 13, 3, 3 / sf, 3 / sf, image[0].ravel())
+    assert np.abs(c.inference(10).reshape(H, W, M) - want[0]).max() <= TOL
+    top2 = np.sort(want[0], -1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 4 * TOL
+    assert np.array_equal(c.map(10).reshape(H, W)[clear], want[0].argmax(-1)[clear])
+    # SRG with the same label count
+    labels = np.zeros((B, M), np.float32)
+    labels[:, [0, 5, M - 1]] = 1
+    probs = np.ascontiguousarray(np.transpose(want, (0, 3, 1, 2)))
+    cues = (rng.rand(B, M, H, W) < 0.01).astype(np.float32)
+    seeds = eng.srg_host(labels, probs, cues, 0.99, 0.3)
+    for b in range(B):
+        assert np.array_equal(seeds[b], srg_oracle.srg_closed_form(labels[b], cues[b], probs[b], 0.99, 0.3))
+    eng.close()
 
 
 @pytest.mark.parametrize("n_iters", [0, 1, 2, 3])
@@ -237,7 +284,7 @@ def test_densecrf_objects_share_one_engine(torch_cuda):
             top2 = np.sort(want, axis=2)[:, :, -2:]
             assert ((top2[:, :, 1] - top2[:, :, 0])[bad] <= 4e-4).all()
     with pytest.raises(api.DsrgError):
-        api.DenseCRF(8, 8, 33)
+        api.DenseCRF(8, 8, 256)              # DSRG_MAX_LABELS_WIDE = 255
     _lib.lib().dsrg_densecrf_release_engines()
     got = cases[0][0].inference(10)            # the pool is re-created on demand
     assert np.isfinite(got).all()
