@@ -103,7 +103,7 @@ static int lattice_alloc(Engine *e, Lattice &L, int d, int shared) {
     L.maxloc = (d == 2) ? kMaxLocSp : kMaxLocBi;
     const size_t nt = n * e->ntiles;
     rc |= dalloc(e, &L.tl_nloc, nt);
-    L.entcap = 256 * (d + 1) + L.maxloc;  // every segment is padded to an even entry count
+    L.entcap = kTileThreads * (d + 1) + L.maxloc;  // every segment is padded to an even entry count
     rc |= dalloc(e, &L.tl_hdr, nt * L.maxloc);
     rc |= dalloc(e, &L.tl_pack, nt * L.entcap);
     rc |= dalloc(e, &L.tl_loc, n * (d + 1) * L.N);

@@ -80,7 +80,11 @@ enum KTag {
 // ---- lattice.cu ----
 int lattice_build(Engine *e, Lattice &L, int B, const uint8_t *image_dev, cudaStream_t s);
 // ---- tiles.cu ----
-constexpr int kTileW = 32, kTileH = 8;       // one thread per pixel, one warp per tile row
+#ifndef DSRG_TILE_H
+#define DSRG_TILE_H 8
+#endif
+constexpr int kTileW = 32, kTileH = DSRG_TILE_H;   // one thread per pixel, one warp per tile row
+constexpr int kTileThreads = kTileW * kTileH;
 #ifndef DSRG_MAXLOC_BI
 #define DSRG_MAXLOC_BI 192
 #endif
@@ -97,7 +101,10 @@ constexpr int kTileW = 32, kTileH = 8;       // one thread per pixel, one warp p
 #ifndef DSRG_ROW_PAD
 #define DSRG_ROW_PAD 1
 #endif
-constexpr int kMaxLocSp = 128, kMaxLocBi = DSRG_MAXLOC_BI;
+#ifndef DSRG_MAXLOC_SP
+#define DSRG_MAXLOC_SP 128
+#endif
+constexpr int kMaxLocSp = DSRG_MAXLOC_SP, kMaxLocBi = DSRG_MAXLOC_BI;
 constexpr int kSplatUnroll = DSRG_SPLAT_UNROLL;
 int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s);
 // ---- meanfield.cu ----

@@ -144,8 +144,8 @@ struct TileSmem {
     static constexpr int CH = MP / 4;
     static constexpr int CHP = CH + DSRG_ROW_PAD;
     static constexpr int kRows = kMaxLocSp + kMaxLocBi;
-    static constexpr int kBufF4 = (kRows * CHP > 256 * CHP) ? kRows * CHP : 256 * CHP;  // staged rows / Q alias
-    static constexpr int kEntSp = 256 * 3 + kMaxLocSp, kEntBi = 256 * 6 + kMaxLocBi;  // segments padded to even
+    static constexpr int kBufF4 = (kRows * CHP > kTileThreads * CHP) ? kRows * CHP : kTileThreads * CHP;  // staged rows / Q alias
+    static constexpr int kEntSp = kTileThreads * 3 + kMaxLocSp, kEntBi = kTileThreads * 6 + kMaxLocBi;  // segments padded to even
     float4 buf[kBufF4];
     int2 ent[kEntSp + kEntBi];  // CSR entries (byte offset of the pixel's Q row, weight bits)
     uint64_t bar;
@@ -228,10 +228,10 @@ __device__ __forceinline__ void tile_splat_csr(float4 *vout_sp, float4 *vout_bi,
         return __ldg((s ? hdr_sp : hdr_bi) + (s ? p : p - pairs_sp) / LPV);
     };
     int2 hn = threadIdx.x < pairs ? hdr_of(threadIdx.x) : make_int2(0, 0);
-    for (int p = threadIdx.x; p < pairs; p += 256) {
+    for (int p = threadIdx.x; p < pairs; p += kTileThreads) {
         const bool is_sp = p < pairs_sp;
         const int2 h = hn;  // (first entry | count << 16, local row id)
-        if (p + 256 < pairs) hn = hdr_of(p + 256);
+        if (p + kTileThreads < pairs) hn = hdr_of(p + kTileThreads);
         // segments start on even entries and are padded to an even count (weight-0 entry): two per load
         const int4 *ep = reinterpret_cast<const int4 *>((is_sp ? ent_sp : ent_bi) + (h.x & 0xffff));
         const int n2 = ((h.x >> 16) + 1) >> 1;
@@ -272,7 +272,7 @@ __device__ __forceinline__ void tile_splat_direct(float4 *vout, const int32_t *o
 }
 
 template <int MP, int MODE>
-__global__ void __launch_bounds__(256, DSRG_TILE_CTAS)
+__global__ void __launch_bounds__(kTileThreads, DSRG_TILE_CTAS)
 k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
           float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles, int tile_w, int b0) {
     constexpr int CH = MP / 4;
@@ -306,7 +306,7 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    for (int i = tid; i < n_sp + n_bi; i += 256) {  // up to 128 + 256 local vertices
+    for (int i = tid; i < n_sp + n_bi; i += kTileThreads) {  // up to kMaxLocSp + kMaxLocBi local vertices
         const bool is_sp = i < n_sp;
         const int lv = is_sp ? i : i - n_sp;
         const int2 h = __ldg((is_sp ? hdr_sp : hdr_bi) + lv);
@@ -704,15 +704,15 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
             dim3 gt(e->ntiles, nb);
             if (it == 0) {
                 DSRG_LAUNCH(e, T_MF_TILE, st,
-                            (k_mf_tile<MP, MODE_FIRST><<<gt, 256, smem, st>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M,
+                            (k_mf_tile<MP, MODE_FIRST><<<gt, kTileThreads, smem, st>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M,
                                                                               N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));
             } else if (it < T) {
                 DSRG_LAUNCH(e, T_MF_TILE, st,
-                            (k_mf_tile<MP, MODE_MID><<<gt, 256, smem, st>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M,
+                            (k_mf_tile<MP, MODE_MID><<<gt, kTileThreads, smem, st>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M,
                                                                             N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));
             } else {
                 DSRG_LAUNCH(e, T_MF_TILE, st,
-                            (k_mf_tile<MP, MODE_LAST><<<gt, 256, smem, st>>>(Usrc, Urw, tclamp, e->Q0, vsp, vbi, c_sp, c_bi, M,
+                            (k_mf_tile<MP, MODE_LAST><<<gt, kTileThreads, smem, st>>>(Usrc, Urw, tclamp, e->Q0, vsp, vbi, c_sp, c_bi, M,
                                                                              N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));
                 continue;
             }

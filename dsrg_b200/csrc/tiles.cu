@@ -15,18 +15,20 @@
 namespace dsrg {
 
 template <int DP1, int MAXLOC, int MP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTileThreads)
 k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *tl_nloc, int2 *tl_hdr,
              int2 *tl_pack, uint16_t *tl_loc, float *wn, int N, int W, int H, int tiles_x, int ntiles,
              int entcap, int tile_w) {
-    constexpr int HS = 2048;  // >= 256*DP1 distinct rows in the worst case, power of two
-    static_assert(MAXLOC <= 256, "one scan element per thread");
+    constexpr int HS = kTileThreads * 8;  // >= kTileThreads*DP1 distinct rows in the worst case, power of two
+    constexpr int HBITS = (HS == 1024) ? 10 : (HS == 2048) ? 11 : (HS == 4096) ? 12 : -1;
+    static_assert(HBITS > 0, "hash size");
+    static_assert(MAXLOC <= kTileThreads, "one scan element per thread");
     __shared__ int hkey[HS];
     __shared__ int hlv[HS];
     __shared__ int rows_s[MAXLOC];
     __shared__ int cnt[MAXLOC];
     __shared__ int ptr[MAXLOC + 1];
-    __shared__ int wsum[8];
+    __shared__ int wsum[kTileThreads / 32];
     __shared__ int perm[MAXLOC];
     __shared__ int scnt[MAXLOC];
     __shared__ int count;
@@ -36,7 +38,7 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
     const int x = tx * tile_w + (tid & 31), y = ty * kTileH + (tid >> 5);
     const bool in = (tid & 31) < tile_w && x < W && y < H;
     const int pix = y * W + x;
-    for (int i = tid; i < HS; i += 256) hkey[i] = -1;
+    for (int i = tid; i < HS; i += kTileThreads) hkey[i] = -1;
     if (tid < MAXLOC) cnt[tid] = 0;
     if (tid == 0) count = 0;
     __syncthreads();
@@ -51,7 +53,7 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
             const int row = off[at];
             w[r] = __fmul_rn(bary[at], nrm);
             wn[at] = w[r];
-            unsigned s = ((unsigned)row * 2654435761u) >> 21;  // 11 bits
+            unsigned s = ((unsigned)row * 2654435761u) >> (32 - HBITS);
             while (true) {
                 int old = atomicCAS(&hkey[s], -1, row);
                 if (old == -1) {
@@ -137,7 +139,7 @@ int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s) {
     dim3 g(e->ntiles, nb);
 #define DSRG_TILE_BUILD(DP1, MAXLOC, MPV)                                                                   \
     DSRG_LAUNCH(e, T_LAT_MISC, s,                                                                            \
-                (k_tile_build<DP1, MAXLOC, MPV><<<g, 256, 0, s>>>(L.off, L.bary, L.norm, L.tl_nloc, L.tl_hdr, \
+                (k_tile_build<DP1, MAXLOC, MPV><<<g, kTileThreads, 0, s>>>(L.off, L.bary, L.norm, L.tl_nloc, L.tl_hdr, \
                                                                   L.tl_pack, L.tl_loc, L.wn, L.N, e->W, e->H,  \
                                                                   e->tiles_x, e->ntiles, L.entcap, e->tile_w)))
 #define DSRG_TILE_BUILD_MP(MPV)                           \
