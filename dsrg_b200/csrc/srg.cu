@@ -48,8 +48,11 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
 // MT > 0: the label count is a compile-time constant, so all 2*MT loads of a pixel are issued before the
 // first use (the kernel is a stream of 2*MT planes and was latency-bound at 41 % of DRAM peak);
 // MT == 0: generic run-time loop.
+#ifndef DSRG_SRG_LABEL_CTAS
+#define DSRG_SRG_LABEL_CTAS 1
+#endif
 template <int MT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, DSRG_SRG_LABEL_CTAS)
 k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, const float *__restrict__ cues,
             double th1, double th2, int renorm, uint8_t *lmap, uint8_t *lflag, int32_t *parent, uint8_t *hc,
             int32_t *label_map_out, int Mrt, int N, int W) {
@@ -80,6 +83,12 @@ k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, c
                 pv[c] = __ldg(pb + (size_t)c * N);
             }
         }
+        // float64 sum of the clamped values in NumPy's order (common.cuh:numpy_sum), formed on the fly when the label
+        // count is a compile-time constant in [8, 128]: eight accumulators over the first MT - MT % 8 values, their
+        // fixed combination tree, then the tail
+        constexpr bool kInline = MT >= 8 && MT <= 128;
+        constexpr int kBody = MT - MT % 8;
+        double r8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int c = 0; c < M; c++) {
             const float cu = MT ? cuv[MT ? c : 0] : cb[(size_t)c * N];
@@ -90,18 +99,29 @@ k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, c
             }
             double v = (double)(MT ? pv[MT ? c : 0] : pb[(size_t)c * N]);
             if (renorm && v < 0.0001) v = 0.0001;
+            if (kInline && renorm) {
+                if (c < 8) r8[c & 7] = v;
+                else if (c < kBody) r8[c & 7] += v;
+                else {
+                    if (c == kBody) s = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+                    s += v;
+                }
+            }
             if (lab[c] == 1.0f && (cstar < 0 || v > best)) {
                 best = v;
                 cstar = c;
             }
         }
         if (renorm) {
-            // float64 sum of the clamped values in NumPy's order (common.cuh:numpy_sum)
-            auto clamped = [&](int c) {
-                const double v = (double)(MT ? pv[MT ? c : 0] : pb[(size_t)c * N]);
-                return v < 0.0001 ? 0.0001 : v;
-            };
-            s = numpy_sum<MT>(clamped, M);
+            if (kInline) {
+                if (MT == kBody) s = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+            } else {
+                auto clamped = [&](int c) {
+                    const double v = (double)(MT ? pv[MT ? c : 0] : pb[(size_t)c * N]);
+                    return v < 0.0001 ? 0.0001 : v;
+                };
+                s = numpy_sum<MT>(clamped, M);
+            }
             best = best / s;
         }
         // thresholds (pylayers.py:251-257): strict > in float64; overwrite the seed label
