@@ -171,7 +171,10 @@ k_srg_merge(const uint8_t *lmap, int32_t *parent, int N, int W) {
     if (i >= W) {
         const int n = i - W;
         if (lm[n] == L) {
-            uf_union(par, i, n);  // N covers NW and NE through the row above
+            // N covers NW and NE through the row above.  The link is redundant when the pixel to the left and the
+            // one above it carry the same label: (i-1, n-1) then joins the same two horizontal runs -- by induction
+            // the leftmost pixel of such a stretch makes the link, the rest skip their root chases
+            if (!(x > 0 && lm[i - 1] == L && lm[n - 1] == L)) uf_union(par, i, n);
         } else {
             if (x > 0 && lm[n - 1] == L) uf_union(par, i, n - 1);
             if (x < W - 1 && lm[n + 1] == L) uf_union(par, i, n + 1);
