@@ -349,9 +349,16 @@ def run_b200(args, rank, local_rank, world):
     if sampler:
         torch.cuda.synchronize()
         sampler.mark()
-    ms = timed(step, args.steps)
+    # EXACTLY K steps per timed block (barrier + synchronize on both sides, max over ranks).  A block of the default
+    # K is a fraction of a second, so the block is repeated until ~1.5 s of GPU time has been sampled (at most 9
+    # blocks) and the MEDIAN block is reported: the number does not hang on one quarter-second window and the clock
+    # sampler sees dozens of samples under load.
+    trials = [timed(step, args.steps)]
+    while len(trials) < 9 and sum(trials) < 1500.0:
+        trials.append(timed(step, args.steps))
     clocks = sampler.stop() if sampler else None
-    launches = eng.take_launch_count()
+    launches = eng.take_launch_count() // len(trials)
+    ms = float(np.median(trials))
     value = images_per_step * args.steps / (ms * 1e-3)
 
     # per-kernel durations by CUDA events on the launching stream, same K steps repeated
@@ -423,17 +430,24 @@ def run_b200(args, rank, local_rank, world):
         h2d, d2h = per_image_h2d * sum(sizes), per_image_d2h * sum(sizes)
         for _ in range(1 if sweep else 2):
             host_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            host_step()          # synchronises its own stream before returning
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        def host_block():
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                host_step()          # synchronises its own stream before returning
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dt], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt
+        dts = [host_block()]
+        while len(dts) < 7 and sum(dts) < 1.5 and not sweep:
+            dts.append(host_block())
+        dt = float(np.median(dts))
         e2e = {"value": images_per_step * args.steps / dt, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+               "timed_blocks": len(dts),
                "d2h_bytes_per_step": int(d2h), "api": "dsrg_*_host (C ABI, pinned host buffers)",
                "note": "inputs are re-sent from the same pinned buffers every step; the in-place 1e-4 clamp of probs "
                        "(pylayers.py:312) therefore only changes values during the first warm-up step"}
@@ -539,6 +553,8 @@ def run_b200(args, rank, local_rank, world):
                        "thresholds": [TH1, TH2], "images": "%s, cam-like cues, 8 distinct images repeated" % IMAGE_VARIANT,
                        "l2": "inputs larger than L2 (%.0f MB of probs+cues per step)" % (2 * 4 * M * N * B / 1e6),
                        "parallelism": "dp%d (images shard, no data-path collective)" % world},
+            "timed_blocks": {"n": len(trials), "steps_each": args.steps, "ms_per_step": [round(t / args.steps, 4) for t in trials],
+                             "reported": "median block"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "kernels": kernels, "cpu_baseline": cpu_baseline, **extras,
         }))
