@@ -632,6 +632,28 @@ int dsrg_srg_batch_dev(dsrg_engine *h, int B, const float *labels, const float *
                    (cudaStream_t)stream);
 }
 
+}  // extern "C"
+
+namespace dsrg {
+// the full pass; cues / seeds as float planes or (host pipeline, wire.cu) in the 1-bit wire format
+int dsrg_forward_core(Engine *e, int B, const float *labels, float *probs, const float *cues, const uint32_t *cue_bits,
+                      const uint8_t *image, const dsrg_crf_params *params, double th1, double th2, float *seeds_out,
+                      uint32_t *seed_bits, float *crf_out, cudaStream_t s) {
+    GraphKey key = pass_key(e, 3, B, params);
+    key.add(labels).add(probs).add(cues).add(cue_bits).add(image).add(th1).add(th2).add(seeds_out).add(seed_bits).add(crf_out);
+    return crf_pass_done(e, B, run_pass(e, s, key, spatial_ready(e, params), [&]() {
+        // refinement (pylayers.py:310-331): in-place clamp, unary = probs (NCHW), CRF
+        int r = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
+        if (r) return r;
+        if (crf_out && (r = meanfield_export(e, B, crf_out, DSRG_LAYOUT_NCHW, s))) return r;
+        // SRG on the raw marginals with the float64 clamp + renormalisation fused in (renorm = 1)
+        return srg_run(e, B, labels, e->Qcur, cues, th1, th2, 1, seeds_out, nullptr, s, cue_bits, seed_bits);
+    }));
+}
+}  // namespace dsrg
+
+extern "C" {
+
 int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *probs,
                           const float *cues, const uint8_t *image, const dsrg_crf_params *params,
                           double th1, double th2, float *seeds_out, float *crf_out, void *stream) {
@@ -643,17 +665,8 @@ int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *pro
         set_error("NULL pointer argument");
         return DSRG_E_INVALID;
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    GraphKey key = pass_key(e, 3, B, params);
-    key.add(labels).add(probs).add(cues).add(image).add(th1).add(th2).add(seeds_out).add(crf_out);
-    return crf_pass_done(e, B, run_pass(e, s, key, spatial_ready(e, params), [&]() {
-        // refinement (pylayers.py:310-331): in-place clamp, unary = probs (NCHW), CRF
-        int r = crf_core(e, B, probs, DSRG_LAYOUT_NCHW, true, probs, image, params, s);
-        if (r) return r;
-        if (crf_out && (r = meanfield_export(e, B, crf_out, DSRG_LAYOUT_NCHW, s))) return r;
-        // SRG on the raw marginals with the float64 clamp + renormalisation fused in (renorm = 1)
-        return srg_run(e, B, labels, e->Qcur, cues, th1, th2, 1, seeds_out, nullptr, s);
-    }));
+    return dsrg_forward_core(e, B, labels, probs, cues, nullptr, image, params, th1, th2, seeds_out, nullptr, crf_out,
+                             (cudaStream_t)stream);
 }
 
 int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t *image,

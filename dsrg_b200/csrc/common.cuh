@@ -120,7 +120,11 @@ int meanfield_export_renorm(Engine *e, int B, float *result_out, float *log_out,
 // ---- srg.cu ----
 int srg_run(Engine *e, int B, const float *labels, const float *probs, const float *cues,
             double th1, double th2, int renorm, float *seeds_out, int32_t *label_map_out,
-            cudaStream_t s);
+            cudaStream_t s, const uint32_t *cue_bits = nullptr, uint32_t *seed_bits = nullptr);
+// ---- api.cu: the full pass with optional 1-bit cue / seed planes (wire.cu) ----
+int dsrg_forward_core(Engine *e, int B, const float *labels, float *probs, const float *cues, const uint32_t *cue_bits,
+                      const uint8_t *image, const dsrg_crf_params *params, double th1, double th2, float *seeds_out,
+                      uint32_t *seed_bits, float *crf_out, cudaStream_t s);
 // ---- loss.cu ----
 int seedloss_forward(Engine *e, int B, const float *probs, const float *seeds, float *terms_out,
                      cudaStream_t s);

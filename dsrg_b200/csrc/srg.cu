@@ -51,9 +51,20 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
 #ifndef DSRG_SRG_LABEL_CTAS
 #define DSRG_SRG_LABEL_CTAS 1
 #endif
-template <int MT>
+// cue planes come either as float32 (the reference's blobs) or as 1 bit per value (the host pipeline's wire format,
+// wire.cu: bit c*N + i of image b's words): CB selects the reader
+template <bool CB>
+__device__ __forceinline__ float cue_at(const float *cues_f, const uint32_t *cues_b, size_t img_base_f, size_t img_base_w,
+                                        int c, int N, int i) {
+    if (!CB) return __ldg(cues_f + img_base_f + (size_t)c * N + i);
+    const size_t g = (size_t)c * N + i;
+    return (__ldg(cues_b + img_base_w + (g >> 5)) >> (g & 31)) & 1u ? 1.0f : 0.0f;
+}
+
+template <int MT, bool CB>
 __global__ void __launch_bounds__(kThreads, DSRG_SRG_LABEL_CTAS)
 k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, const float *__restrict__ cues,
+            const uint32_t *__restrict__ cue_bits, int wpi,
             double th1, double th2, int renorm, uint8_t *lmap, uint8_t *lflag, int32_t *parent, uint8_t *hc,
             int32_t *label_map_out, int Mrt, int N, int W) {
     const int M = MT ? MT : Mrt;
@@ -64,7 +75,7 @@ k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, c
     if (in) {
         const float *lab = labels + (size_t)b * M;
         const float *pb = probs + (size_t)b * M * N + i;
-        const float *cb = cues + (size_t)b * M * N + i;
+        const size_t cbase_f = (size_t)b * M * N, cbase_w = (size_t)b * wpi;
         // One pass over the classes.  With renorm the reference divides every clamped value by the
         // float64 sum s (pylayers.py:328-330) before taking the arg-max over the PRESENT classes
         // (first index wins ties, pylayers.py:240-243).  IEEE division by a common positive s is
@@ -79,7 +90,7 @@ k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, c
         if (MT) {
 #pragma unroll
             for (int c = 0; c < (MT ? MT : 1); c++) {
-                cuv[c] = __ldg(cb + (size_t)c * N);
+                cuv[c] = cue_at<CB>(cues, cue_bits, cbase_f, cbase_w, c, N, i);
                 pv[c] = __ldg(pb + (size_t)c * N);
             }
         }
@@ -91,7 +102,7 @@ k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, c
         double r8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int c = 0; c < M; c++) {
-            const float cu = MT ? cuv[MT ? c : 0] : cb[(size_t)c * N];
+            const float cu = MT ? cuv[MT ? c : 0] : cue_at<CB>(cues, cue_bits, cbase_f, cbase_w, c, N, i);
             nseed += cu;
             if (cu > 0.0f) {  // seeds: the highest class index wins (pylayers.py:248-250)
                 L = c + 1;
@@ -127,7 +138,7 @@ k_srg_label(const float *__restrict__ labels, const float *__restrict__ probs, c
         // thresholds (pylayers.py:251-257): strict > in float64; overwrite the seed label
         if (cstar >= 0 && best > th2 && (cstar != 0 || best > th1)) {
             L = cstar + 1;
-            cue_at_L = cb[(size_t)cstar * N];
+            cue_at_L = cue_at<CB>(cues, cue_bits, cbase_f, cbase_w, cstar, N, i);
         }
         uint8_t fl = 0;
         if (L > 0) {
@@ -195,55 +206,97 @@ k_srg_flag(const uint8_t *lflag, int32_t *parent, uint8_t *hc, int N) {
 }
 
 // K4 --------------------------------------------------------------------------------------------
-template <int MT>
+// seeds = cues OR (grown AND NOT excluded).  CB: cues are bits; SB: seeds are written as bits (into zeroed words:
+// a warp's 32 pixels of one class are 32 consecutive bits that straddle at most two words -> two atomicOr by lane 0)
+template <int MT, bool CB, bool SB>
 __global__ void __launch_bounds__(kThreads)
-k_srg_emit(const float *__restrict__ cues, const uint8_t *lmap, const uint8_t *lflag, const int32_t *parent,
-           const uint8_t *hc, float *__restrict__ seeds_out, int Mrt, int N) {
+k_srg_emit(const float *__restrict__ cues, const uint32_t *__restrict__ cue_bits, int wpi, const uint8_t *lmap,
+           const uint8_t *lflag, const int32_t *parent, const uint8_t *hc, float *__restrict__ seeds_out,
+           uint32_t *__restrict__ seed_bits, int Mrt, int N) {
     const int M = MT ? MT : Mrt;
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const size_t p = (size_t)b * N + i;
-    const int L = lmap[p];
+    const bool in = i < N;
+    if (!SB && !in) return;  // the bit writer needs whole warps for its ballots
+    const size_t p = (size_t)b * N + (in ? i : 0);
     int grow_c = -1;
-    if (L > 0 && !(lflag[p] & 2)) {
-        const int root = parent[p];  // fully compressed by K3
-        if (hc[(size_t)b * N + root]) grow_c = L - 1;
+    if (in) {
+        const int L = lmap[p];
+        if (L > 0 && !(lflag[p] & 2)) {
+            const int root = parent[p];  // fully compressed by K3
+            if (hc[(size_t)b * N + root]) grow_c = L - 1;
+        }
     }
-    const float *cb = cues + (size_t)b * M * N + i;
+    const size_t cbase_f = (size_t)b * M * N, cbase_w = (size_t)b * wpi;
     float *ob = seeds_out + (size_t)b * M * N + i;
+    const int i0 = i & ~31;  // first pixel of this warp (blocks start at multiples of 256)
     if (MT) {
         float v[MT ? MT : 1];
 #pragma unroll
-        for (int c = 0; c < (MT ? MT : 1); c++) v[c] = __ldg(cb + (size_t)c * N);
+        for (int c = 0; c < (MT ? MT : 1); c++) v[c] = in ? cue_at<CB>(cues, cue_bits, cbase_f, cbase_w, c, N, i) : 0.0f;
 #pragma unroll
-        for (int c = 0; c < (MT ? MT : 1); c++) ob[(size_t)c * N] = (c == grow_c) ? 1.0f : v[c];
+        for (int c = 0; c < (MT ? MT : 1); c++) {
+            const float o = (c == grow_c) ? 1.0f : v[c];
+            if (!SB) {
+                ob[(size_t)c * N] = o;
+            } else {
+                const unsigned m = __ballot_sync(0xffffffffu, in && o != 0.0f);
+                if ((threadIdx.x & 31) == 0 && m) {
+                    const size_t g0 = (size_t)c * N + i0;
+                    const int sh = (int)(g0 & 31);
+                    atomicOr(seed_bits + cbase_w + (g0 >> 5), m << sh);
+                    if (sh && (m >> (32 - sh))) atomicOr(seed_bits + cbase_w + (g0 >> 5) + 1, m >> (32 - sh));
+                }
+            }
+        }
     } else {
-        for (int c = 0; c < M; c++) ob[(size_t)c * N] = (c == grow_c) ? 1.0f : cb[(size_t)c * N];
+        for (int c = 0; c < M; c++) {
+            const float o = (c == grow_c) ? 1.0f : (in ? cue_at<CB>(cues, cue_bits, cbase_f, cbase_w, c, N, i) : 0.0f);
+            if (!SB) {
+                ob[(size_t)c * N] = o;
+            } else {
+                const unsigned m = __ballot_sync(0xffffffffu, in && o != 0.0f);
+                if ((threadIdx.x & 31) == 0 && m) {
+                    const size_t g0 = (size_t)c * N + i0;
+                    const int sh = (int)(g0 & 31);
+                    atomicOr(seed_bits + cbase_w + (g0 >> 5), m << sh);
+                    if (sh && (m >> (32 - sh))) atomicOr(seed_bits + cbase_w + (g0 >> 5) + 1, m >> (32 - sh));
+                }
+            }
+        }
     }
 }
 
+// cue_bits / seed_bits (optional): the planes in the host pipeline's 1-bit wire format (wpi words per image) instead of
+// float32 -- saves expanding the cues to floats and packing the seeds again on the device
 int srg_run(Engine *e, int B, const float *labels, const float *probs, const float *cues,
             double th1, double th2, int renorm, float *seeds_out, int32_t *label_map_out,
-            cudaStream_t s) {
+            cudaStream_t s, const uint32_t *cue_bits, uint32_t *seed_bits) {
     const int N = e->N, M = e->M;
+    const int wpi = (int)(((size_t)M * N + 31) / 32);
     dim3 g(cdiv(N, kThreads), B);
-    if (M == 21)
-        DSRG_LAUNCH(e, T_SRG_LABEL, s,
-                    k_srg_label<21><<<g, kThreads, 0, s>>>(labels, probs, cues, th1, th2, renorm, e->lmap, e->lflag,
-                                                           e->parent, e->hc, label_map_out, M, N, e->W));
-    else
-        DSRG_LAUNCH(e, T_SRG_LABEL, s,
-                    k_srg_label<0><<<g, kThreads, 0, s>>>(labels, probs, cues, th1, th2, renorm, e->lmap, e->lflag,
-                                                          e->parent, e->hc, label_map_out, M, N, e->W));
+#define DSRG_LABEL(MTV, CBV)                                                                                          \
+    DSRG_LAUNCH(e, T_SRG_LABEL, s,                                                                                     \
+                (k_srg_label<MTV, CBV><<<g, kThreads, 0, s>>>(labels, probs, cues, cue_bits, wpi, th1, th2, renorm, e->lmap, \
+                                                              e->lflag, e->parent, e->hc, label_map_out, M, N, e->W)))
+    if (M == 21) { if (cue_bits) DSRG_LABEL(21, true); else DSRG_LABEL(21, false); }
+    else { if (cue_bits) DSRG_LABEL(0, true); else DSRG_LABEL(0, false); }
+#undef DSRG_LABEL
     DSRG_LAUNCH(e, T_SRG_MERGE, s, k_srg_merge<<<g, kThreads, 0, s>>>(e->lmap, e->parent, N, e->W));
     DSRG_LAUNCH(e, T_SRG_FLAG, s, k_srg_flag<<<g, kThreads, 0, s>>>(e->lflag, e->parent, e->hc, N));
-    if (M == 21)
-        DSRG_LAUNCH(e, T_SRG_EMIT, s,
-                    k_srg_emit<21><<<g, kThreads, 0, s>>>(cues, e->lmap, e->lflag, e->parent, e->hc, seeds_out, M, N));
-    else
-        DSRG_LAUNCH(e, T_SRG_EMIT, s,
-                    k_srg_emit<0><<<g, kThreads, 0, s>>>(cues, e->lmap, e->lflag, e->parent, e->hc, seeds_out, M, N));
+    if (seed_bits) DSRG_CUDA_TRY(cudaMemsetAsync(seed_bits, 0, (size_t)B * wpi * sizeof(uint32_t), s));
+#define DSRG_EMIT(MTV, CBV, SBV)                                                                                       \
+    DSRG_LAUNCH(e, T_SRG_EMIT, s,                                                                                      \
+                (k_srg_emit<MTV, CBV, SBV><<<g, kThreads, 0, s>>>(cues, cue_bits, wpi, e->lmap, e->lflag, e->parent, e->hc, \
+                                                                  seeds_out, seed_bits, M, N)))
+#define DSRG_EMIT_MT(MTV)                                              \
+    if (cue_bits && seed_bits) DSRG_EMIT(MTV, true, true);             \
+    else if (cue_bits) DSRG_EMIT(MTV, true, false);                    \
+    else if (seed_bits) DSRG_EMIT(MTV, false, true);                   \
+    else DSRG_EMIT(MTV, false, false)
+    if (M == 21) { DSRG_EMIT_MT(21); } else { DSRG_EMIT_MT(0); }
+#undef DSRG_EMIT_MT
+#undef DSRG_EMIT
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }

@@ -365,22 +365,19 @@ static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *pro
         DSRG_CUDA_TRY(cudaStreamWaitEvent(s, e->pipe_events[3 * c], 0));
         mark(s);
         dim3 gb(cdiv(n_img, kThreads), nb);
-        if (ok)
-            DSRG_LAUNCH(e, T_WIRE, s,
-                        k_bits_to_float<<<gb, kThreads, 0, s>>>(e->d_cbits + (size_t)b0 * wpi, e->st_cues + o, n_img, (int)wpi));
+        // packed cues / seeds stay packed: the SRG kernels read and write the 1-bit planes directly (srg.cu)
+        const uint32_t *cbits = ok ? e->d_cbits + (size_t)b0 * wpi : nullptr;
+        uint32_t *sbits = ok_s ? e->d_sbits + (size_t)b0 * wpi : nullptr;
         if (ok_m)  // before the pass clamps the device copy in place
             DSRG_LAUNCH(e, T_WIRE, s,
                         k_float_to_bits<1><<<gb, kThreads, 0, s>>>(e->st_unary + o, e->d_mbits + (size_t)b0 * wpi, n_img, (int)wpi));
         if (srg_only)
-            rc = dsrg_srg_batch_dev(h, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o, th1, th2,
-                                    renorm, e->st_out + o, label_map_out ? e->st_lmap + (size_t)b0 * e->N : nullptr, s);
+            rc = srg_run(e, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o, th1, th2, renorm,
+                         e->st_out + o, label_map_out ? e->st_lmap + (size_t)b0 * e->N : nullptr, s, cbits, sbits);
         else
-            rc = dsrg_dsrg_forward_dev(h, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o,
-                                       e->st_image + (size_t)b0 * e->N * 3, params, th1, th2, e->st_out + o, nullptr, s);
+            rc = dsrg_forward_core(e, nb, e->st_labels + (size_t)b0 * e->M, e->st_unary + o, e->st_cues + o, cbits,
+                                   e->st_image + (size_t)b0 * e->N * 3, params, th1, th2, e->st_out + o, sbits, nullptr, s);
         if (rc) return rc;
-        if (ok_s)
-            DSRG_LAUNCH(e, T_WIRE, s,
-                        k_float_to_bits<0><<<gb, kThreads, 0, s>>>(e->st_out + o, e->d_sbits + (size_t)b0 * wpi, n_img, (int)wpi));
         if (crf_out) {  // raw marginals of this chunk, parked in the (now consumed) cues staging area
             if ((rc = meanfield_export(e, nb, e->st_cues + o, DSRG_LAYOUT_NCHW, s))) return rc;
         }
