@@ -278,20 +278,26 @@ static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *pro
         }
     }
     if (cb0.empty()) {
-        // default: B/16, 3B/16, then quarters (4 | 12 | 16 | 16 | 16 of 64).  The GPU is the slower stage of the
-        // pipeline (0.5 ms + 0.235 ms per image and chunk against 0.17 ms per image of PCIe at 321x321x21), so a
-        // short first chunk gets it going early and the rest must be big enough to keep its kernels efficient:
-        // measured best of the schedules in profiles/r2_host_schedule_sweep.txt once a chunk's ~130 launches are
-        // replayed as one CUDA graph (round 1, plain launches: 8 | 24 | 32).  A positive host_chunk caps the size.
+        // default: five chunks that grow (5 | 9 | 13 | 17 | 20 of 64; boundaries at 8 %, 22 %, 42 %, 69 % of the batch).
+        // The GPU is the slower stage of the pipeline (0.5 ms + 0.235 ms per image and chunk against 0.17 ms per image
+        // of PCIe at 321x321x21): a short first chunk gets it going early, later chunks must be big enough to keep
+        // its kernels efficient, and the last one not so big that its D2H + unpack tail shows.  Best of the schedules
+        // in profiles/r2_host_schedule_sweep.txt once a chunk's ~130 launches are replayed as one CUDA graph (round 1,
+        // plain launches: 8 | 24 | 32).  A positive host_chunk caps the chunk size.
         const int cap = e->host_chunk > 0 ? e->host_chunk : B;
-        const int want[3] = {(B + 15) / 16, (3 * B + 15) / 16, (B + 3) / 4};
-        for (int b = 0, k = 0; b < B; k++) {
-            int nb = want[k < 2 ? k : 2];
-            if (nb > cap) nb = cap;
-            if (nb > B - b) nb = B - b;
-            cb0.push_back(b);
-            cnb.push_back(nb);
-            b += nb;
+        const double edge[5] = {5.0 / 64, 14.0 / 64, 27.0 / 64, 44.0 / 64, 1.0};
+        for (int b = 0, k = 0; b < B;) {
+            int end = k < 5 ? (int)(edge[k] * B + 0.5) : B;
+            k++;
+            if (end <= b) continue;
+            if (end > B || k >= 5) end = B;
+            while (b < end) {
+                int nb = end - b;
+                if (nb > cap) nb = cap;
+                cb0.push_back(b);
+                cnb.push_back(nb);
+                b += nb;
+            }
         }
     }
     const int nchunks = (int)cb0.size();
