@@ -233,6 +233,20 @@ int crf_core_for_post(Engine *e, const float *unary_hwc, const uint8_t *image, c
     return crf_core(e, 1, unary_hwc, DSRG_LAYOUT_NHWC, false, nullptr, image, p, s);
 }
 
+// Graph replay for the per-image callers (inference post-processing, DenseCRF objects), whose image size changes
+// from call to call: when the shared spatial lattice is not the one this call needs, the pass that rebuilds it is
+// captured as such (`rebuild` is part of the key), so its graph is self-contained and valid whatever the engine
+// worked on in between; `after` restores the host-side notes a replay skips.
+bool post_pass_needs_spatial(const Engine *e, const dsrg_crf_params *p) { return !spatial_ready(e, p); }
+void post_pass_done(Engine *e, const dsrg_crf_params *p, int B, int rc) {
+    if (rc == DSRG_OK && p) {
+        e->sp.sigma[0] = p->theta_gamma_x;
+        e->sp.sigma[1] = p->theta_gamma_y;
+        e->sp_valid = true;
+    }
+    crf_pass_done(e, B, rc);
+}
+
 int ensure_staging(Engine *e) {
     if (e->st_unary) return DSRG_OK;
     const size_t n = (size_t)e->maxB * e->M * e->Ncap;
@@ -456,9 +470,8 @@ int dsrg_engine_set_size(dsrg_engine *h, int H, int W) {
     DSRG_CUDA_TRY(cudaDeviceSynchronize());
     engine_shape(e, H, W);
     e->last_crf_B = 0;
-    // graphs are keyed by the shape and hold its strides; the few an engine keeps are cheap to rebuild, and the
-    // per-image callers that re-shape on every call see each shape too rarely to profit from them
-    graph_clear(e);
+    // cached graphs stay: they are keyed by the shape (every stride is a function of it and of the capacity the
+    // buffers were sized for), so a per-image caller that meets a size again replays that size's graph
     return DSRG_OK;
 }
 
@@ -983,7 +996,15 @@ static int densecrf_run(dsrg_densecrf *c, int n_iters, Engine **eng) {
         return meanfield_run(e, 1, e->st_unary, DSRG_LAYOUT_NHWC, false, nullptr, p0, s);
     }
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image, c->image.data(), c->image.size(), cudaMemcpyHostToDevice, s));
-    return crf_core(e, 1, e->st_unary, DSRG_LAYOUT_NHWC, false, nullptr, e->st_image, &c->params, s);
+    const bool rebuild = post_pass_needs_spatial(e, &c->params);
+    GraphKey key = pass_key(e, 7, 1, &c->params);
+    key.add(rebuild);
+    if (rebuild) e->sp_valid = false;
+    rc = run_pass(e, s, key, true, [&]() {
+        return crf_core(e, 1, e->st_unary, DSRG_LAYOUT_NHWC, false, nullptr, e->st_image, &c->params, s);
+    });
+    post_pass_done(e, &c->params, 1, rc);
+    return rc;
 }
 
 int dsrg_densecrf_inference(dsrg_densecrf *c, int n_iters, float *probs_out) {

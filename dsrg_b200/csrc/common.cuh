@@ -125,6 +125,8 @@ int srg_run(Engine *e, int B, const float *labels, const float *probs, const flo
 int dsrg_forward_core(Engine *e, int B, const float *labels, float *probs, const float *cues, const uint32_t *cue_bits,
                       const uint8_t *image, const dsrg_crf_params *params, double th1, double th2, float *seeds_out,
                       uint32_t *seed_bits, float *crf_out, cudaStream_t s);
+bool post_pass_needs_spatial(const Engine *e, const dsrg_crf_params *p);
+void post_pass_done(Engine *e, const dsrg_crf_params *p, int B, int rc);
 // ---- loss.cu ----
 int seedloss_forward(Engine *e, int B, const float *probs, const float *seeds, float *terms_out,
                      cudaStream_t s);

@@ -119,6 +119,40 @@ int zoom_scores(Engine *e, const float *in, int hi, int wi, float *out, int accu
 int crf_core_for_post(Engine *e, const float *unary_hwc, const uint8_t *image, const dsrg_crf_params *p,
                       cudaStream_t s);  // api.cu
 
+static int predict_mask_body(Engine *e, int mode, int n_scales, const float *const *scores, const int *hs, const int *ws,
+                             const uint8_t *image, float eps, int smooth, const dsrg_crf_params *p, const LabelSel &sel,
+                             int32_t *result, float *probs_out, cudaStream_t s) {
+    int rc;
+    const int N = e->N, M = e->M;
+    float *unary = e->st_unary;                       // [H][W][M]
+    float *clamped = smooth ? nullptr : (probs_out ? probs_out : e->st_out);
+    if (mode == DSRG_POST_SUM_SCORES) {
+        for (int k = 0; k < n_scales; k++)
+            if ((rc = zoom_scores(e, scores[k], hs[k], ws[k], unary, k > 0, s))) return rc;
+        DSRG_LAUNCH(e, T_POST, s,
+                    k_post_softmax<true><<<cdiv(N, kThreads), kThreads, 0, s>>>(unary, unary, clamped, N, M, 1, M, eps));
+    } else {
+        const int np = hs[0] * ws[0];
+        float *small = e->st_cues;                    // [M][h][w] probabilities at network resolution
+        DSRG_LAUNCH(e, T_POST, s,
+                    k_post_softmax<false><<<cdiv(np, kThreads), kThreads, 0, s>>>(scores[0], small, nullptr, np, M,
+                                                                                   np, 1, eps));
+        if ((rc = zoom_scores(e, small, hs[0], ws[0], unary, 0, s))) return rc;
+        const long long n = (long long)N * M;
+        DSRG_LAUNCH(e, T_POST, s, k_post_clamp_log<<<cdiv(n, kThreads), kThreads, 0, s>>>(unary, unary, clamped, n, eps));
+    }
+    DSRG_CUDA_TRY(cudaGetLastError());
+    if (smooth) {
+        if ((rc = crf_core_for_post(e, unary, image, p, s))) return rc;
+        if (probs_out && (rc = meanfield_export(e, 1, probs_out, DSRG_LAYOUT_NHWC, s))) return rc;
+        DSRG_LAUNCH(e, T_POST, s, k_post_argmax<<<cdiv(N, kThreads), kThreads, 0, s>>>(e->Qcur, result, N, N, 1, sel));
+    } else {
+        DSRG_LAUNCH(e, T_POST, s, k_post_argmax<<<cdiv(N, kThreads), kThreads, 0, s>>>(clamped, result, N, 1, M, sel));
+    }
+    DSRG_CUDA_TRY(cudaGetLastError());
+    return DSRG_OK;
+}
+
 static int predict_mask(Engine *e, int mode, int n_scales, const float *const *scores, const int *hs,
                         const int *ws, const uint8_t *image, float eps, int smooth, const dsrg_crf_params *p,
                         const int32_t *labels_sel, int n_sel, int32_t *result, float *probs_out,
@@ -152,34 +186,18 @@ static int predict_mask(Engine *e, int mode, int n_scales, const float *const *s
         }
     int rc = ensure_staging(e);
     if (rc) return rc;
-    const int N = e->N, M = e->M;
-    float *unary = e->st_unary;                       // [H][W][M]
-    float *clamped = smooth ? nullptr : (probs_out ? probs_out : e->st_out);
-    if (mode == DSRG_POST_SUM_SCORES) {
-        for (int k = 0; k < n_scales; k++)
-            if ((rc = zoom_scores(e, scores[k], hs[k], ws[k], unary, k > 0, s))) return rc;
-        DSRG_LAUNCH(e, T_POST, s,
-                    k_post_softmax<true><<<cdiv(N, kThreads), kThreads, 0, s>>>(unary, unary, clamped, N, M, 1, M, eps));
-    } else {
-        const int np = hs[0] * ws[0];
-        float *small = e->st_cues;                    // [M][h][w] probabilities at network resolution
-        DSRG_LAUNCH(e, T_POST, s,
-                    k_post_softmax<false><<<cdiv(np, kThreads), kThreads, 0, s>>>(scores[0], small, nullptr, np, M,
-                                                                                   np, 1, eps));
-        if ((rc = zoom_scores(e, small, hs[0], ws[0], unary, 0, s))) return rc;
-        const long long n = (long long)N * M;
-        DSRG_LAUNCH(e, T_POST, s, k_post_clamp_log<<<cdiv(n, kThreads), kThreads, 0, s>>>(unary, unary, clamped, n, eps));
-    }
-    DSRG_CUDA_TRY(cudaGetLastError());
-    if (smooth) {
-        if ((rc = crf_core_for_post(e, unary, image, p, s))) return rc;
-        if (probs_out && (rc = meanfield_export(e, 1, probs_out, DSRG_LAYOUT_NHWC, s))) return rc;
-        DSRG_LAUNCH(e, T_POST, s, k_post_argmax<<<cdiv(N, kThreads), kThreads, 0, s>>>(e->Qcur, result, N, N, 1, sel));
-    } else {
-        DSRG_LAUNCH(e, T_POST, s, k_post_argmax<<<cdiv(N, kThreads), kThreads, 0, s>>>(clamped, result, N, 1, M, sel));
-    }
-    DSRG_CUDA_TRY(cudaGetLastError());
-    return DSRG_OK;
+    // the whole post-processing of one image as one graph per (shape, score sizes, options): the evaluation tools
+    // meet the same few dozen image sizes over and over (api.cu:post_pass_needs_spatial)
+    const bool rebuild = smooth && post_pass_needs_spatial(e, p);
+    GraphKey key;
+    key.add(6).add(e->H).add(e->W).add(mode).add(n_scales).add(image).add(eps).add(smooth).add(result).add(probs_out).add(rebuild);
+    for (int k = 0; k < n_scales; k++) key.add(scores[k]).add(hs[k]).add(ws[k]);
+    if (smooth) key.add(*p);
+    for (int k = 0; k < sel.n; k++) key.add(sel.id[k]);
+    if (rebuild) e->sp_valid = false;
+    rc = run_pass(e, s, key, true, [&]() { return predict_mask_body(e, mode, n_scales, scores, hs, ws, image, eps, smooth, p, sel, result, probs_out, s); });
+    if (smooth) post_pass_done(e, p, 1, rc);
+    return rc;
 }
 
 static int grow_raw(Engine *e, size_t need) {

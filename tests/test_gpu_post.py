@@ -181,3 +181,36 @@ def test_crf_function_many_sizes_one_engine(torch_cuda):
         want = crf_oracle.CRF(p["image"], np.log(pr), scale_factor=1.0)
         assert np.abs(got - want).max() <= TOL
     assert len(pool._ENGINES) == 1
+
+
+def test_per_image_callers_replay_graphs_across_sizes(torch_cuda):
+    """The evaluation tools meet the same image sizes again and again: the post-processing of one image and a
+    DenseCRF object's inference are replayed as CUDA graphs per size (post.cu:predict_mask, api.cu:densecrf_run),
+    also when another size ran on the shared engine in between (the replayed graph then contains the rebuild of
+    the shared spatial lattice).  Results equal the plain launches up to the float atomics' noise."""
+    import fake_caffe
+    fake_caffe.install()
+    import krahenbuhl2013
+    pool.clear()
+    cases = [synth.make_score_blobs(40 + i, H, W, (31, 41)) for i, (H, W) in enumerate([(90, 120), (120, 90), (75, 100)])]
+    crf_cases = []
+    for i, (H, W) in enumerate([(60, 80), (80, 60)]):
+        p = synth.make_problem(900 + i, H, W, image="smooth")
+        pr = np.transpose(p["probs"], (1, 2, 0)).copy()
+        pr[pr < 1e-5] = 1e-5
+        crf_cases.append((p["image"], np.log(pr)))
+    eng = pool.engine_for(120, 120, 21)
+    eng.set_graphs(False)
+    want = [postprocess.predict_mask_ms(c["image"], c["blobs"], return_probs=True) for c in cases]
+    want_crf = [krahenbuhl2013.CRF(im, u, scale_factor=1.0) for im, u in crf_cases]
+    eng.set_graphs(True)
+    r0 = eng.graph_replays
+    for rnd in range(4):
+        for c, (wl, wp) in zip(cases, want):
+            lab, pr = postprocess.predict_mask_ms(c["image"], c["blobs"], return_probs=True)
+            assert np.abs(pr - wp).max() <= TOL
+            labels_agree(lab, wl, wp)
+        for (im, u), w in zip(crf_cases, want_crf):
+            assert np.abs(krahenbuhl2013.CRF(im, u, scale_factor=1.0) - w).max() <= TOL
+    assert eng is pool.engine_for(120, 120, 21)          # still the one pooled engine
+    assert eng.graph_replays - r0 >= 2 * (len(cases) + len(crf_cases))   # rounds 3 and 4 are replays
