@@ -51,6 +51,7 @@ SIGNATURES = {
     "dsrg_engine_set_graphs": (_i, [_vp, _i]),
     "dsrg_engine_graph_replays": (_ll, [_vp]),
     "dsrg_engine_take_launch_count": (_ll, [_vp]),
+    "dsrg_engine_hybrid_tiles": (_ll, [_vp]),
     "dsrg_crf_batch_dev": (_i, [_vp, _i, _vp, _i, _vp, _pp, _vp, _i, _vp]),
     "dsrg_crf_batch_host": (_i, [_vp, _i, _vp, _i, _vp, _pp, _vp, _i]),
     "dsrg_crf_map_batch_dev": (_i, [_vp, _i, _vp, _i, _vp, _pp, _vp, _vp]),

@@ -125,6 +125,14 @@ class Engine(object):
     def set_lanes(self, lanes):
         check(self._L.dsrg_engine_set_lanes(self.h, int(lanes)))
 
+    @property
+    def hybrid_tiles(self):
+        """Tiles of the last mean-field pass that took the hybrid path (textured images); synchronises."""
+        n = int(self._L.dsrg_engine_hybrid_tiles(self.h))
+        if n < 0:
+            raise DsrgError(_lib.last_error())
+        return n
+
     def take_launch_count(self):
         return int(self._L.dsrg_engine_take_launch_count(self.h))
 

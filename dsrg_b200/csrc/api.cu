@@ -100,9 +100,10 @@ static int lattice_alloc(Engine *e, Lattice &L, int d, int shared) {
     rc |= dalloc(e, &L.vcount, n);
     rc |= dalloc(e, &L.rowbase, (size_t)e->maxB + 1);
     rc |= dalloc(e, &L.nbr, (size_t)(d + 1) * L.nbr_stride);
-    L.maxloc = (d == 2) ? kMaxLocSp : kMaxLocBi;
+    L.maxloc = (d == 2) ? kMaxLocSp : kMaxLocHy;
     const size_t nt = n * e->ntiles;
     rc |= dalloc(e, &L.tl_nloc, nt);
+    rc |= dalloc(e, &L.tl_hy, nt);
     L.entcap = kTileThreads * (d + 1) + L.maxloc;  // every segment is padded to an even entry count
     rc |= dalloc(e, &L.tl_hdr, nt * L.maxloc);
     rc |= dalloc(e, &L.tl_pack, nt * L.entcap);
@@ -110,6 +111,7 @@ static int lattice_alloc(Engine *e, Lattice &L, int d, int shared) {
     rc |= dalloc(e, &L.wn, n * (d + 1) * L.N);
     if (rc) return DSRG_E_NOMEM;
     if (cudaMemset(L.hkeys, 0xFF, sizeof(uint64_t) * n * L.cap) != cudaSuccess) return DSRG_E_CUDA;
+    if (cudaMemset(L.tl_hy, 0, nt) != cudaSuccess) return DSRG_E_CUDA;
     if (cudaMemset(L.hval, 0xFF, sizeof(int32_t) * n * L.cap) != cudaSuccess) return DSRG_E_CUDA;
     return DSRG_OK;
 }
@@ -125,6 +127,7 @@ static void lattice_free(Lattice &L) {
     cudaFree(L.rowbase);
     cudaFree(L.nbr);
     cudaFree(L.tl_nloc);
+    cudaFree(L.tl_hy);
     cudaFree(L.tl_hdr);
     cudaFree(L.tl_pack);
     cudaFree(L.tl_loc);
@@ -404,6 +407,9 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     rc |= dalloc(e, &e->hc, bn);
     rc |= dalloc(e, &e->loss_acc, (size_t)max_batch * 4);
     rc |= dalloc(e, &e->dev_err, 1);
+    rc |= dalloc(e, &e->hy_list, (size_t)max_batch * e->ntiles);
+    rc |= dalloc(e, &e->hy_count, 1);
+    if (!rc && cudaMemset(e->hy_count, 0, sizeof(int)) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaMemset(e->dev_err, 0, sizeof(int)) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaStreamCreateWithFlags(&e->in_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
@@ -432,7 +438,7 @@ void dsrg_engine_destroy(dsrg_engine *h) {
     lattice_free(e->sp);
     lattice_free(e->bi);
     void *ptrs[] = {e->U, e->Q0, e->spA, e->spB, e->spC, e->biA, e->biB, e->biC, e->nvA, e->nvB, e->lmap,
-                    e->lflag, e->parent, e->hc, e->loss_acc, e->dev_err, e->st_unary, e->st_out,
+                    e->lflag, e->parent, e->hc, e->loss_acc, e->dev_err, e->hy_list, e->hy_count, e->st_unary, e->st_out,
                     e->st_cues, e->st_labels, e->st_image, e->st_lmap, e->st_raw, e->st_idx};
     for (void *p : ptrs) cudaFree(p);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -499,7 +505,7 @@ long long dsrg_engine_take_launch_count(dsrg_engine *h) {
 static const char *kTagNames[T_COUNT] = {
     "lattice_insert", "lattice_misc", "lattice_norm", "mf_init", "mf_zero", "mf_blur_spatial",
     "mf_blur_bilateral", "mf_tile", "mf_export", "srg_label", "srg_merge", "srg_flag", "srg_emit",
-    "seedloss", "wire_bits", "prepare_image", "postprocess", "annotation", "mf_blur_fused"};
+    "seedloss", "wire_bits", "prepare_image", "postprocess", "annotation", "mf_blur_fused", "mf_tile_hybrid"};
 
 int dsrg_profile_tag_count(void) { return T_COUNT; }
 
@@ -525,6 +531,18 @@ int dsrg_engine_set_graphs(dsrg_engine *h, int enable) {
 }
 
 long long dsrg_engine_graph_replays(const dsrg_engine *h) { return h ? ((const Engine *)h)->graph_replays : 0; }
+long long dsrg_engine_hybrid_tiles(dsrg_engine *h) {
+    Engine *e = (Engine *)h;
+    if (!e) return -1;
+    DeviceScope dev_scope(e);
+    int n = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(&n, e->hy_count, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("reading the hybrid-tile count failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    return n;
+}
 
 int dsrg_engine_set_lanes(dsrg_engine *h, int lanes) {
     Engine *e = (Engine *)h;
@@ -576,11 +594,18 @@ int dsrg_crf_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layo
     cudaStream_t s = (cudaStream_t)stream;
     GraphKey key = pass_key(e, 1, B, params);
     key.add(unary).add(unary_layout).add(image).add(out).add(out_layout);
-    return crf_pass_done(e, B, run_pass(e, s, key, spatial_ready(e, params), [&]() {
+    // krahenbuhl2013.CRF runs on this entry point with a size that changes from call to call: like the other
+    // per-image callers its graph carries the rebuild of the shared spatial lattice when one is due
+    const bool rebuild = params && post_pass_needs_spatial(e, params);
+    key.add(rebuild);
+    if (rebuild) e->sp_valid = false;
+    rc = run_pass(e, s, key, params != nullptr, [&]() {
         int r = crf_core(e, B, unary, unary_layout, false, nullptr, image, params, s);
         if (r) return r;
         return meanfield_export(e, B, out, out_layout, s);
-    }));
+    });
+    post_pass_done(e, params, B, rc);
+    return rc;
 }
 
 int dsrg_crf_map_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layout,

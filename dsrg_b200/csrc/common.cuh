@@ -56,8 +56,9 @@ struct Lattice {
     long long nbr_stride = 0;   // rows per axis in nbr
     // tile-local view (32x8-pixel tiles): the distinct vertices a tile touches, so that splat and
     // slice run out of shared memory (see tiles.cu)
-    int maxloc = 0;                // local-vertex capacity per tile; tiles beyond it use the fallback
-    int32_t *tl_nloc = nullptr;    // [nimg][ntiles] distinct vertices of the tile, -1 = overflow
+    int maxloc = 0;                // local-vertex capacity per tile (kMaxLocSp / kMaxLocHy)
+    int32_t *tl_nloc = nullptr;    // [nimg][ntiles] local vertices of the tile | kTileHybrid if other incidences go direct
+    uint8_t *tl_hy = nullptr;      // [nimg][ntiles] 1: hybrid tile, k_mf_tile skips it (bilateral only)
     int2 *tl_hdr = nullptr;        // [nimg][ntiles][maxloc] per local vertex: (first entry | count<<16, local row id)
     int2 *tl_pack = nullptr;       // [nimg][ntiles][entcap] CSR entries grouped by local vertex:
                                    // (byte offset of the pixel's Q row in the tile, weight bits)
@@ -74,7 +75,7 @@ struct Engine;
 enum KTag {
     T_LAT_INSERT = 0, T_LAT_MISC, T_LAT_NORM, T_MF_INIT, T_MF_ZERO, T_MF_BLUR_SP,
     T_MF_BLUR_BI, T_MF_TILE, T_MF_EXPORT, T_SRG_LABEL, T_SRG_MERGE, T_SRG_FLAG, T_SRG_EMIT,
-    T_LOSS, T_WIRE, T_PREP, T_POST, T_ANNOT, T_MF_BLUR_FUSED, T_COUNT
+    T_LOSS, T_WIRE, T_PREP, T_POST, T_ANNOT, T_MF_BLUR_FUSED, T_MF_TILE_HY, T_COUNT
 };
 
 // ---- lattice.cu ----
@@ -104,9 +105,33 @@ constexpr int kTileThreads = kTileW * kTileH;
 #ifndef DSRG_MAXLOC_SP
 #define DSRG_MAXLOC_SP 128
 #endif
-constexpr int kMaxLocSp = DSRG_MAXLOC_SP, kMaxLocBi = DSRG_MAXLOC_BI;
+// hybrid tiles (more distinct bilateral vertices than DSRG_MAXLOC_BI) are run by their own kernel, k_mf_tile_hy,
+// DSRG_HY_CTAS CTAs per SM with room for DSRG_MAXLOC_HY local vertices; the other incidences go direct
+#ifndef DSRG_MAXLOC_HY
+#define DSRG_MAXLOC_HY 256
+#endif
+#ifndef DSRG_HY_CTAS
+#define DSRG_HY_CTAS 3
+#endif
+constexpr int kMaxLocSp = DSRG_MAXLOC_SP, kMaxLocBi = DSRG_MAXLOC_BI, kMaxLocHy = DSRG_MAXLOC_HY;
+static_assert(kMaxLocHy >= kMaxLocBi, "a hybrid tile holds at least what a plain one does");
 constexpr int kSplatUnroll = DSRG_SPLAT_UNROLL;
+// tl_loc value of a (pixel, vertex) incidence that is NOT in the tile-local list, and the flag in tl_nloc of a tile
+// that has such incidences (a hybrid tile, tiles.cu)
+constexpr int kLocRemote = 0xFFFF, kTileHybrid = 1 << 16;
+// an overflow tile becomes a hybrid one when its local list would cover at least this share (percent) of its
+// incidences; below that (uniform-noise images, the sigma/12 training lattices) the plain direct path is faster
+// ... and only when the batch has at least DSRG_HY_MIN_TILES hybrid tiles per SM (tiles.cu: k_tile_demote)
+#ifndef DSRG_HY_MIN_TILES
+#define DSRG_HY_MIN_TILES 8
+#endif
+#ifndef DSRG_HY_MIN_COVER
+#define DSRG_HY_MIN_COVER 40
+#endif
 int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s);
+// hybrid tiles pay off only when the batch has enough tiles to keep the GPU busy: small passes (the 41x41 training
+// shape: 240 tiles) are launch-bound and every overflow tile stays on k_mf_tile's direct path
+inline bool hybrid_tiles_on(const Engine *e, int B);
 // ---- meanfield.cu ----
 int meanfield_run(Engine *e, int B, const float *unary, int unary_layout, bool clamp_inplace,
                   float *unary_rw, const dsrg_crf_params &p, cudaStream_t s);
@@ -153,6 +178,8 @@ struct Engine {
     float *spA = nullptr, *spB = nullptr, *spC = nullptr, *biA = nullptr, *biB = nullptr, *biC = nullptr;
     int tiles_x = 0, tiles_y = 0, ntiles = 0;  // tiles of tile_w x 8 pixels
     int tile_w = 32;  // <= 32: the image width is split evenly so that no sliver tiles remain
+    int2 *hy_list = nullptr;   // [maxB * ntiles] (tile, image) of the hybrid tiles of the current lattices
+    int *hy_count = nullptr;   // their number (device-resident)
     // 1-channel buffers for the normalisation pass
     float *nvA = nullptr, *nvB = nullptr;
     // SRG state
@@ -192,6 +219,10 @@ struct Engine {
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
 };
+
+inline bool hybrid_tiles_on(const Engine *e, int B) {
+    return e->MP <= DSRG_MAX_LABELS && (long long)e->ntiles * B >= 4LL * e->sm_count;
+}
 
 // RAII bracket around one kernel launch: counts it and, when profiling is on, times it with a pair
 // of CUDA events on the launching stream.

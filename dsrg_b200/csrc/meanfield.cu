@@ -81,6 +81,7 @@ struct TileLat {
     const int32_t *rowbase;  // [B+1]
     // tile-local view (tiles.cu)
     const int32_t *tl_nloc;
+    const uint8_t *tl_hy;    // [nimg][ntiles] 1: hybrid tile (bilateral view only)
     const int2 *tl_hdr;
     const int2 *tl_pack;
     const uint16_t *tl_loc;
@@ -140,12 +141,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 
 template <int MP>
+struct TileRow {
+    static constexpr int CH = MP / 4;
+    static constexpr int CHP = CH + DSRG_ROW_PAD;  // float4 per staged row (padded)
+};
+
+template <int MP, int MAXBI = kMaxLocBi>
 struct TileSmem {
     static constexpr int CH = MP / 4;
-    static constexpr int CHP = CH + DSRG_ROW_PAD;
-    static constexpr int kRows = kMaxLocSp + kMaxLocBi;
+    static constexpr int CHP = TileRow<MP>::CHP;
+    static constexpr int kRows = kMaxLocSp + MAXBI;
     static constexpr int kBufF4 = (kRows * CHP > kTileThreads * CHP) ? kRows * CHP : kTileThreads * CHP;  // staged rows / Q alias
-    static constexpr int kEntSp = kTileThreads * 3 + kMaxLocSp, kEntBi = kTileThreads * 6 + kMaxLocBi;  // segments padded to even
+    static constexpr int kEntSp = kTileThreads * 3 + kMaxLocSp, kEntBi = kTileThreads * 6 + MAXBI;  // segments padded to even
     float4 buf[kBufF4];
     int2 ent[kEntSp + kEntBi];  // CSR entries (byte offset of the pixel's Q row, weight bits)
     uint64_t bar;
@@ -157,7 +164,7 @@ struct TileSmem {
 template <int MP, int DP1>
 __device__ __forceinline__ void tile_slice_smem(const float4 *vs, const uint16_t *loc, size_t stride,
                                                 const float *w, float coef, float *t, bool tail1) {
-    constexpr int CH = MP / 4, CHP = TileSmem<MP>::CHP;
+    constexpr int CH = MP / 4, CHP = TileRow<MP>::CHP;
 #pragma unroll
     for (int r = 0; r < DP1; r++) {
         const float4 *row = vs + (int)__ldg(loc + r * stride) * CHP;
@@ -202,6 +209,54 @@ __device__ __forceinline__ void tile_slice_global(const float4 *vin, const int32
             t[4 * c + 3] = fmaf(wr, v.w, t[4 * c + 3]);
         }
     }
+}
+
+// hybrid tiles (tiles.cu): an incidence whose vertex is in the tile-local list is sliced from the staged rows, the
+// others (tl_loc == kLocRemote) straight from the global value rows; returns the mask of the remote ones
+template <int MP, int DP1>
+__device__ __forceinline__ unsigned tile_slice_mixed(const float4 *vs, const uint16_t *loc, const float4 *vin,
+                                                     const int32_t *off, size_t stride, int base, const float *w,
+                                                     float coef, float *t) {
+    constexpr int CH = MP / 4, CHP = TileRow<MP>::CHP;
+    unsigned remote = 0;  // bit r: incidence r of this pixel goes direct
+#pragma unroll
+    for (int r = 0; r < DP1; r++) {
+        const int l = (int)__ldg(loc + r * stride);
+        const float wr = coef * w[r];
+        if (l != kLocRemote) {
+            const float4 *row = vs + l * CHP;
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const float4 v = row[c];
+                t[4 * c + 0] = fmaf(wr, v.x, t[4 * c + 0]);
+                t[4 * c + 1] = fmaf(wr, v.y, t[4 * c + 1]);
+                t[4 * c + 2] = fmaf(wr, v.z, t[4 * c + 2]);
+                t[4 * c + 3] = fmaf(wr, v.w, t[4 * c + 3]);
+            }
+        } else {
+            remote |= 1u << r;
+            const float4 *row = vin + (size_t)(base + __ldg(off + r * stride)) * CH;
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const float4 v = __ldg(row + c);
+                t[4 * c + 0] = fmaf(wr, v.x, t[4 * c + 0]);
+                t[4 * c + 1] = fmaf(wr, v.y, t[4 * c + 1]);
+                t[4 * c + 2] = fmaf(wr, v.z, t[4 * c + 2]);
+                t[4 * c + 3] = fmaf(wr, v.w, t[4 * c + 3]);
+            }
+        }
+    }
+    return remote;
+}
+
+// which incidences of this pixel are remote (first iteration: nothing is sliced)
+template <int DP1>
+__device__ __forceinline__ unsigned tile_remote_mask(const uint16_t *loc, size_t stride) {
+    unsigned remote = 0;
+#pragma unroll
+    for (int r = 0; r < DP1; r++)
+        if ((int)__ldg(loc + r * stride) == kLocRemote) remote |= 1u << r;
+    return remote;
 }
 
 // CSR splat of both lattices: one thread per (local vertex, label quad) walks the vertex's segment
@@ -271,6 +326,22 @@ __device__ __forceinline__ void tile_splat_direct(float4 *vout, const int32_t *o
     }
 }
 
+// direct splat of one pixel's remote incidences (hybrid tiles): MP/4 vector reductions per such row
+template <int MP, int DP1>
+__device__ __forceinline__ void tile_splat_remote(float4 *vout, unsigned remote, const int32_t *off, size_t stride,
+                                                  int base, const float *w, const float *q) {
+    constexpr int CH = MP / 4;
+#pragma unroll
+    for (int r = 0; r < DP1; r++) {
+        if (!(remote >> r & 1u)) continue;
+        float4 *row = vout + (size_t)(base + __ldg(off + r * stride)) * CH;
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+            atomicAdd(row + c, make_float4(w[r] * q[4 * c], w[r] * q[4 * c + 1], w[r] * q[4 * c + 2],
+                                           w[r] * q[4 * c + 3]));
+    }
+}
+
 template <int MP, int MODE>
 __global__ void __launch_bounds__(kTileThreads, DSRG_TILE_CTAS)
 k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
@@ -280,6 +351,11 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     using SM = TileSmem<MP>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM &sm = *reinterpret_cast<SM *>(smem_raw);
+    // A hybrid tile is k_mf_tile_hy's.  The test reads a byte map of its own and stands before anything else: the
+    // same test on the tile's vertex count, wherever it was placed, made ptxas allocate this kernel's 64 registers
+    // differently (more spill traffic in the splat loop; B200: 0.765 -> 0.81 ms per launch on images that have no
+    // such tile at all).
+    if (bi.tl_hy[(size_t)(b0 + blockIdx.y) * ntiles + blockIdx.x]) return;
     const int tile = blockIdx.x, b = b0 + blockIdx.y, tid = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int x = tx * tile_w + (tid & 31), y = ty * kTileH + (tid >> 5);
@@ -293,7 +369,7 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     const int base_sp = sp.rowbase[b], base_bi = bi.rowbase[b];
     constexpr int CHP = SM::CHP;
     float4 *vs_sp = sm.buf, *vs_bi = sm.buf + kMaxLocSp * CHP;
-    const int2 *hdr_sp = sp.tl_hdr + ti_sp * kMaxLocSp, *hdr_bi = bi.tl_hdr + ti_bi * kMaxLocBi;  // global, L1/L2-resident
+    const int2 *hdr_sp = sp.tl_hdr + ti_sp * kMaxLocSp, *hdr_bi = bi.tl_hdr + ti_bi * kMaxLocHy;  // global, L1/L2-resident
     int2 *ent_sp = sm.ent, *ent_bi = sm.ent + SM::kEntSp;
     const size_t strideN = (size_t)N;
     const size_t px_sp = (size_t)sb_sp * 3 * N + pix, px_bi = (size_t)sb_bi * 6 * N + pix;
@@ -412,6 +488,155 @@ k_mf_tile(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, Tile
     if (fb_bi && in) tile_splat_direct<MP, 6>(vout_bi, bi.off + px_bi, strideN, base_bi, w_bi, t);
     tile_splat_csr<MP>(vout_sp, vout_bi, n_sp, n_bi, hdr_sp, hdr_bi, base_sp, base_bi, ent_sp, ent_bi,
                        reinterpret_cast<const unsigned char *>(qs));
+}
+
+// Hybrid tiles (tiles.cu: more distinct vertices than the shared-memory path of k_mf_tile holds -- textured images,
+// whose vertices are shared in colour space rather than between neighbouring pixels).  A persistent grid walks the
+// list of such tiles: the kMaxLocHy most-touched vertices of a tile go through shared memory exactly like in
+// k_mf_tile (bulk-copied rows, CSR splat), the remaining incidences are sliced from and reduced into global
+// memory straight from the registers.  Its own register / shared-memory budget (DSRG_HY_CTAS CTAs per SM) keeps
+// this code out of k_mf_tile's 64-register allocation.
+template <int MP, int MODE>
+__global__ void __launch_bounds__(kTileThreads, DSRG_HY_CTAS)
+k_mf_tile_hy(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, TileLat sp, TileLat bi, float c_sp,
+             float c_bi, int M, int N, int W, int H, int tiles_x, int ntiles, int tile_w, int b0, int nb,
+             const int2 *hy_list, const int *hy_count) {
+    constexpr int CH = MP / 4;
+    constexpr int kRowBytes = MP * 4;
+    using SM = TileSmem<MP, kMaxLocHy>;
+    constexpr int CHP = SM::CHP;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int nhy = *hy_count;
+    const size_t strideN = (size_t)N;
+    float4 *vs_sp = sm.buf, *vs_bi = sm.buf + kMaxLocSp * CHP;
+    int2 *ent_sp = sm.ent, *ent_bi = sm.ent + SM::kEntSp;
+    float4 *vout_sp = reinterpret_cast<float4 *>(sp.val_out), *vout_bi = reinterpret_cast<float4 *>(bi.val_out);
+    for (int item = blockIdx.x; item < nhy; item += gridDim.x) {
+        const int2 bt = hy_list[item];
+        const int tile = bt.x, b = bt.y;
+        if (b < b0 || b >= b0 + nb) continue;  // another lane's image (block-uniform)
+        const int tx = tile % tiles_x, ty = tile / tiles_x;
+        const int x = tx * tile_w + (tid & 31), y = ty * kTileH + (tid >> 5);
+        const bool in = (tid & 31) < tile_w && x < W && y < H;
+        const int pix = in ? y * W + x : 0;
+        const int sb_sp = sp.shared ? 0 : b, sb_bi = bi.shared ? 0 : b;
+        const size_t ti_sp = (size_t)sb_sp * ntiles + tile, ti_bi = (size_t)sb_bi * ntiles + tile;
+        const int nl_sp = sp.tl_nloc[ti_sp], nl_bi = bi.tl_nloc[ti_bi];
+        // a negative count is an overflow tile that kept no local list: all its incidences are remote
+        const bool hy_sp = nl_sp < 0, hy_bi = true;
+        const int n_sp = nl_sp < 0 ? 0 : nl_sp, n_bi = nl_bi & 0xffff;
+        const int base_sp = sp.rowbase[b], base_bi = bi.rowbase[b];
+        const int2 *hdr_sp = sp.tl_hdr + ti_sp * kMaxLocSp, *hdr_bi = bi.tl_hdr + ti_bi * kMaxLocHy;
+        const size_t px_sp = (size_t)sb_sp * 3 * N + pix, px_bi = (size_t)sb_bi * 6 * N + pix;
+
+        // ---- asynchronous staging of the local vertices' rows and the CSR entry blocks (as in k_mf_tile) ----
+        const int n_copies = (MODE != MODE_FIRST ? n_sp + n_bi : 0) + (MODE != MODE_LAST ? (n_sp > 0) + (n_bi > 0) : 0);
+        if (tid == 0) {
+            mbar_init(&sm.bar, n_copies > 0 ? n_copies : 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        for (int i = tid; i < n_sp + n_bi; i += kTileThreads) {
+            const bool is_sp = i < n_sp;
+            const int lv = is_sp ? i : i - n_sp;
+            const int2 h = __ldg((is_sp ? hdr_sp : hdr_bi) + lv);
+            const int row = (is_sp ? base_sp : base_bi) + h.y;
+            if (MODE != MODE_FIRST) {
+                mbar_arrive_expect_tx(&sm.bar, kRowBytes);
+                bulk_g2s((is_sp ? vs_sp : vs_bi) + lv * CHP, (is_sp ? sp.val_in : bi.val_in) + (size_t)row * MP,
+                         kRowBytes, &sm.bar);
+            }
+            if (MODE != MODE_LAST && lv == (is_sp ? n_sp : n_bi) - 1) {  // the last segment tells the block's length
+                const uint32_t bytes = (uint32_t)((h.x & 0xffff) + (((h.x >> 16) + 1) & ~1)) * 8u;
+                mbar_arrive_expect_tx(&sm.bar, bytes);
+                bulk_g2s(is_sp ? ent_sp : ent_bi,
+                         is_sp ? sp.tl_pack + ti_sp * sp.entcap : bi.tl_pack + ti_bi * bi.entcap, bytes, &sm.bar);
+            }
+        }
+        if (n_copies == 0 && tid == 0) mbar_arrive_expect_tx(&sm.bar, 0);
+
+        // ---- per-pixel data ----
+        float t[MP];
+        {
+            const size_t ub = (size_t)b * M * N + pix;
+            const float *Ub = U + ub;
+#pragma unroll
+            for (int k = 0; k < MP; k++) {
+                float v = 0.0f;
+                if (in && k < M) v = (MODE == MODE_FIRST) ? *Ub : __ldg(Ub);
+                if (MODE == MODE_FIRST) {
+                    if (clamp && in && k < M && v < kMinProb) {
+                        v = kMinProb;
+                        U_rw[ub + (size_t)k * N] = v;
+                    }
+                }
+                t[k] = v;
+                Ub += N;
+            }
+        }
+        float w_sp[3], w_bi[6];
+        {
+            const float *p = sp.wn + px_sp;
+#pragma unroll
+            for (int r = 0; r < 3; r++, p += N) w_sp[r] = in ? __ldg(p) : 0.0f;
+            p = bi.wn + px_bi;
+#pragma unroll
+            for (int r = 0; r < 6; r++, p += N) w_bi[r] = in ? __ldg(p) : 0.0f;
+        }
+        mbar_wait(&sm.bar, 0);
+
+        // ---- slice + update ----
+        unsigned rm_sp = 0, rm_bi = 0;  // this pixel's incidences that go direct
+        if (in) {
+            if (MODE != MODE_FIRST) {
+                rm_sp = tile_slice_mixed<MP, 3>(vs_sp, sp.tl_loc + px_sp, reinterpret_cast<const float4 *>(sp.val_in),
+                                                sp.off + px_sp, strideN, base_sp, w_sp, c_sp, t);
+                rm_bi = tile_slice_mixed<MP, 6>(vs_bi, bi.tl_loc + px_bi, reinterpret_cast<const float4 *>(bi.val_in),
+                                                bi.off + px_bi, strideN, base_bi, w_bi, c_bi, t);
+            } else {
+                if (hy_sp) rm_sp = tile_remote_mask<3>(sp.tl_loc + px_sp, strideN);
+                if (hy_bi) rm_bi = tile_remote_mask<6>(bi.tl_loc + px_bi, strideN);
+            }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < MP; k++)
+            if (k < M) mx = fmaxf(mx, t[k]);
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < MP; k++) {
+            t[k] = (k < M) ? exp_neg(t[k] - mx) : 0.0f;
+            sum += t[k];
+        }
+        const float inv = __frcp_rn(sum);
+#pragma unroll
+        for (int k = 0; k < MP; k++) t[k] *= inv;
+        if (MODE == MODE_LAST) {
+            if (in) {
+                float *Qb = Qout + (size_t)b * M * N + pix;
+#pragma unroll
+                for (int k = 0; k < MP; k++) {
+                    if (k < M) *Qb = t[k];
+                    Qb += N;
+                }
+            }
+        } else {
+            // ---- splat: remote incidences straight from the registers, the local vertices through the CSR ----
+            if (rm_sp) tile_splat_remote<MP, 3>(vout_sp, rm_sp, sp.off + px_sp, strideN, base_sp, w_sp, t);
+            if (rm_bi) tile_splat_remote<MP, 6>(vout_bi, rm_bi, bi.off + px_bi, strideN, base_bi, w_bi, t);
+            __syncthreads();  // every thread is done reading the staged rows: reuse the buffer for Q
+            float4 *qs = sm.buf;
+#pragma unroll
+            for (int c = 0; c < CH; c++) qs[tid * CHP + c] = make_float4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+            __syncthreads();
+            tile_splat_csr<MP>(vout_sp, vout_bi, n_sp, n_bi, hdr_sp, hdr_bi, base_sp, base_bi, ent_sp, ent_bi,
+                               reinterpret_cast<const unsigned char *>(qs));
+        }
+        __syncthreads();  // the tile is done with the shared buffers and the barrier
+        if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.bar)) : "memory");
+    }
 }
 
 // zero the splat targets of both lattices for images [b0, b0+nb) (row counts are device-resident)
@@ -570,6 +795,7 @@ static TileLat make_tile_view(const Lattice &L, const float *val_in, float *val_
     v.off = L.off;
     v.rowbase = L.rowbase;
     v.tl_nloc = L.tl_nloc;
+    v.tl_hy = L.tl_hy;
     v.tl_hdr = L.tl_hdr;
     v.tl_pack = L.tl_pack;
     v.entcap = L.entcap;
@@ -661,12 +887,16 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
     const float c_sp = p.w2 * alpha_sp, c_bi = p.w1 * alpha_bi;
     static const int smem_pad = getenv("DSRG_B200_TILE_SMEM_PAD") ? atoi(getenv("DSRG_B200_TILE_SMEM_PAD")) : 0;  // occupancy probe
     const size_t smem = sizeof(TileSmem<MP>) + smem_pad;
+    const size_t smem_hy = sizeof(TileSmem<MP, kMaxLocHy>);
     static bool attr_done[64] = {false};   // function attributes are per device
     const int dv = e->device & 63;
     if (!attr_done[dv]) {
         DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile<MP, MODE_LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile_hy<MP, MODE_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hy));
+        DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile_hy<MP, MODE_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hy));
+        DSRG_CUDA_TRY(cudaFuncSetAttribute(k_mf_tile_hy<MP, MODE_LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hy));
         attr_done[dv] = true;
     }
     // Images are independent, so the batch runs as two half-batches on two streams: while one half
@@ -684,6 +914,11 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
 #define DSRG_BLUR_GRID 8
 #endif
     const int bgrid = (DSRG_BLUR_GRID * e->sm_count) / nlanes;
+    // The hybrid tiles of the batch: k_mf_tile_hy, a persistent grid over the device-resident list, issued right
+    // before the plain kernel on the same stream.  A side stream (fork / join around every iteration) cost 8 us per
+    // iteration inside the replayed graph even when the list was empty; an empty launch in line costs 2.
+    const int hgrid = DSRG_HY_CTAS * e->sm_count;
+    const bool hy_on = hybrid_tiles_on(e, B);  // the same test the tile build of this pass made
     // one cooperative launch for all axes of both lattices (single-lane only: two cooperative grids cannot
     // be co-resident)
     const int fmax = nlanes == 1 ? fused_blur_grid<MP>(e) : 0;
@@ -703,15 +938,23 @@ static int run_impl(Engine *e, int B, const float *unary, int layout, bool clamp
             cudaStream_t st = ls[l];
             const int b0 = lb0[l], nb = lnb1[l];
             dim3 gt(e->ntiles, nb);
+#define DSRG_HY_LAUNCH(MODEV, QOUT)                                                                                     \
+    if (hy_on) DSRG_LAUNCH(e, T_MF_TILE_HY, st,                                                                         \
+                (k_mf_tile_hy<MP, MODEV><<<hgrid, kTileThreads, smem_hy, st>>>(Usrc, Urw, tclamp, QOUT, vsp, vbi, c_sp, c_bi, M, N, \
+                                                                          e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0, nb, \
+                                                                          e->hy_list, e->hy_count)))
             if (it == 0) {
+                DSRG_HY_LAUNCH(MODE_FIRST, nullptr);
                 DSRG_LAUNCH(e, T_MF_TILE, st,
                             (k_mf_tile<MP, MODE_FIRST><<<gt, kTileThreads, smem, st>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M,
                                                                               N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));
             } else if (it < T) {
+                DSRG_HY_LAUNCH(MODE_MID, nullptr);
                 DSRG_LAUNCH(e, T_MF_TILE, st,
                             (k_mf_tile<MP, MODE_MID><<<gt, kTileThreads, smem, st>>>(Usrc, Urw, tclamp, nullptr, vsp, vbi, c_sp, c_bi, M,
                                                                             N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));
             } else {
+                DSRG_HY_LAUNCH(MODE_LAST, e->Q0);
                 DSRG_LAUNCH(e, T_MF_TILE, st,
                             (k_mf_tile<MP, MODE_LAST><<<gt, kTileThreads, smem, st>>>(Usrc, Urw, tclamp, e->Q0, vsp, vbi, c_sp, c_bi, M,
                                                                              N, e->W, e->H, e->tiles_x, e->ntiles, e->tile_w, b0)));

