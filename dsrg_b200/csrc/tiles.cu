@@ -29,7 +29,8 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
     __shared__ int rows_s[MAXLOC];
     __shared__ int cnt[MAXLOC];
     __shared__ int ptr[MAXLOC + 1];
-    __shared__ int wsum[kTileThreads / 32];
+    __shared__ int wsum[kTileThreads / 32], wsum2[kTileThreads / 32];
+    __shared__ int sfx[kTileThreads + 1];
     __shared__ int perm[MAXLOC];
     __shared__ int scnt[MAXLOC];
     __shared__ int hist[kTileThreads + 2];
@@ -111,19 +112,40 @@ k_tile_build(const int32_t *off, const float *bary, const float *norm, int32_t *
             for (int i = tid; i < HS; i += kTileThreads)
                 if (hkey[i] != -1) atomicAdd(&hist[hcnt[i]], 1);  // an incidence count is at most kTileThreads
             __syncthreads();
-            if (tid == 0) {
-                int acc = 0, thr = kTileThreads + 1, cov = 0, tot = 0;
-                for (int c = kTileThreads; c >= 1; c--) tot += c * hist[c];
-                for (int c = kTileThreads; c >= 2; c--) {
-                    if (acc + hist[c] > MAXLOC) break;
-                    acc += hist[c];
-                    cov += c * hist[c];
-                    thr = c;
+            // threshold = the smallest incidence count c >= 2 such that the vertices with count >= c fit into MAXLOC:
+            // thread t stands for c = kTileThreads - t, so an inclusive scan over t yields the suffix sums over c
+            {
+                const int c = kTileThreads - tid;
+                int nv = hist[c], ni = c * nv;  // vertices with exactly c incidences, and their incidences
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int a = __shfl_up_sync(0xffffffffu, nv, o), d = __shfl_up_sync(0xffffffffu, ni, o);
+                    if ((tid & 31) >= o) {
+                        nv += a;
+                        ni += d;
+                    }
                 }
-                thr_s = thr;                 // every vertex with >= thr incidences is local,
-                extra_s = (thr - 1 >= 2) ? MAXLOC - acc : 0;  // and the first `extra` ones of the next bucket
-                covered = cov + extra_s * (thr - 1);
-                total = tot;
+                if ((tid & 31) == 31) {
+                    wsum[tid >> 5] = nv;
+                    wsum2[tid >> 5] = ni;
+                }
+                __syncthreads();
+                for (int k = 0; k < (tid >> 5); k++) {
+                    nv += wsum[k];
+                    ni += wsum2[k];
+                }
+                sfx[tid] = nv;
+                __syncthreads();
+                const bool ok = c >= 2 && nv <= MAXLOC;
+                const bool next_ok = (c - 1 >= 2) && sfx[tid + 1] <= MAXLOC;  // tid + 1 <= kTileThreads - 2 here
+                if (ok && !next_ok) {  // exactly one thread: every vertex with >= c incidences is local,
+                    thr_s = c;
+                    const int extra = (c - 1 >= 2) ? MAXLOC - nv : 0;  // and the first `extra` ones of the next bucket
+                    extra_s = extra;
+                    covered = ni + extra * (c - 1);
+                }
+                const int npix = __syncthreads_count(in);
+                if (tid == 0) total = npix * DP1;
             }
             __syncthreads();
             hybrid = covered * 100 >= total * DSRG_HY_MIN_COVER;
