@@ -130,7 +130,8 @@ constexpr int kLocRemote = 0xFFFF, kTileHybrid = 1 << 16;
 #endif
 int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s);
 // hybrid tiles pay off only when the batch has enough tiles to keep the GPU busy: small passes (the 41x41 training
-// shape: 240 tiles) are launch-bound and every overflow tile stays on k_mf_tile's direct path
+// shape: 240 tiles; one VOC-sized image: 800) are launch-bound -- the hybrid kernel's eleven extra launches cost a
+// batch-1 pass 0.1 ms of 1.3 -- and every overflow tile stays on k_mf_tile's direct path
 inline bool hybrid_tiles_on(const Engine *e, int B);
 // ---- meanfield.cu ----
 int meanfield_run(Engine *e, int B, const float *unary, int unary_layout, bool clamp_inplace,
@@ -221,7 +222,7 @@ struct Engine {
 };
 
 inline bool hybrid_tiles_on(const Engine *e, int B) {
-    return e->MP <= DSRG_MAX_LABELS && (long long)e->ntiles * B >= 4LL * e->sm_count;
+    return e->MP <= DSRG_MAX_LABELS && (long long)e->ntiles * B >= 16LL * e->sm_count;
 }
 
 // RAII bracket around one kernel launch: counts it and, when profiling is on, times it with a pair

@@ -262,7 +262,7 @@ k_tile_demote(int2 *hy_list, int *hy_count, int32_t *tl_nloc, uint8_t *tl_hy, in
 int tiles_build(Engine *e, Lattice &L, int nb, cudaStream_t s) {
     dim3 g(e->ntiles, nb);
     const bool hy_on = L.d == 5 && hybrid_tiles_on(e, nb);
-    if (hy_on) DSRG_CUDA_TRY(cudaMemsetAsync(e->hy_count, 0, sizeof(int), s));  // the list of hybrid tiles is rebuilt
+    if (L.d == 5) DSRG_CUDA_TRY(cudaMemsetAsync(e->hy_count, 0, sizeof(int), s));  // the list of hybrid tiles is rebuilt (or stays empty)
 #define DSRG_TILE_BUILD(DP1, MAXA, MAXLOC, MPV)                                                             \
     DSRG_LAUNCH(e, T_LAT_MISC, s,                                                                            \
                 (k_tile_build<DP1, MAXA, MAXLOC, MPV><<<g, kTileThreads, 0, s>>>(L.off, L.bary, L.norm, L.tl_nloc, L.tl_hy, L.tl_hdr, \

@@ -361,17 +361,22 @@ def test_crf_hybrid_tiles_on_textured_images(torch_cuda):
     memory holds.  Such tiles keep their most-touched vertices in a tile-local list and send the other incidences
     straight to global memory (k_mf_tile_hy, csrc/tiles.cu).  Parity with the oracle as everywhere else, for a
     batch that mixes textured and smooth images (both kernels work on the same lattices), replayed as a graph; a
-    batch with only a few overflow tiles hands them back to the plain kernel's direct path."""
+    batch with only a few overflow tiles hands them back to the plain kernel's direct path, and so does a pass
+    that is too small to be worth the extra launches."""
     torch = torch_cuda
     H = W = 321
-    B, M = 4, 21
-    ph = synth.make_batch(3, H, W, image="photo", start=70)
-    sm = synth.make_batch(2, H, W, image="smooth", start=73)
+    B, M = 6, 21
+    ph = synth.make_batch(5, H, W, image="photo", start=70)
+    sm = synth.make_batch(B, H, W, image="smooth", start=75)
     image = np.concatenate([ph["image"][:1], sm["image"][:1], ph["image"][1:]])
     probs = np.concatenate([ph["probs"][:1], sm["probs"][:1], ph["probs"][1:]])
-    pr = np.transpose(probs, (0, 2, 3, 1)).copy()
-    pr[pr < 1e-5] = 1e-5
-    unary = np.log(pr).astype(np.float32)
+
+    def unary_of(p):
+        pr = np.transpose(p, (0, 2, 3, 1)).copy()
+        pr[pr < 1e-5] = 1e-5
+        return np.log(pr).astype(np.float32)
+
+    unary = unary_of(probs)
     want = np.stack([crf_oracle.CRF(image[b], unary[b], 10, 1.0) for b in range(B)])
     eng = api.Engine(B, H, W, M)
     params = api.crf_params(1.0)
@@ -388,15 +393,20 @@ def test_crf_hybrid_tiles_on_textured_images(torch_cuda):
     assert eng.graph_replays >= 2
     ntiles = 11 * 41                               # 30x8-pixel tiles at 321x321
     nh = eng.hybrid_tiles
-    assert 8 * 148 <= nh <= 3 * ntiles + 0.1 * ntiles, nh   # the three textured images, a few tiles of the smooth one
-    # two smooth images alone: their few overflow tiles do not make a hybrid pass
-    pr2 = np.transpose(sm["probs"], (0, 2, 3, 1)).copy()
-    pr2[pr2 < 1e-5] = 1e-5
-    un2 = np.log(pr2).astype(np.float32)
-    want2 = np.stack([want[1], crf_oracle.CRF(sm["image"][1], un2[1], 10, 1.0)])
-    d_out2 = torch.empty((2, H, W, M), dtype=torch.float32, device="cuda")
+    assert 8 * 148 <= nh <= 5 * ntiles + 0.1 * ntiles, nh   # the five textured images, a few tiles of the smooth one
+    # six smooth images: their few overflow tiles do not make a hybrid pass (k_tile_demote)
+    un2 = unary_of(sm["probs"])
+    d_out2 = torch.empty((B, H, W, M), dtype=torch.float32, device="cuda")
     eng.crf_dev(torch.from_numpy(un2).cuda(), torch.from_numpy(sm["image"]).cuda(), params, d_out2)
     torch.cuda.synchronize()
-    assert np.abs(d_out2.cpu().numpy() - want2).max() <= TOL
+    got2 = d_out2.cpu().numpy()
+    assert np.abs(got2[0] - want[1]).max() <= TOL
+    assert np.abs(got2[3] - crf_oracle.CRF(sm["image"][3], un2[3], 10, 1.0)).max() <= TOL
+    assert eng.hybrid_tiles == 0
+    # two textured images alone: a pass below 16 tiles per SM stays on the plain kernel
+    d_out3 = torch.empty((2, H, W, M), dtype=torch.float32, device="cuda")
+    eng.crf_dev(d_un[2:4].contiguous(), d_im[2:4].contiguous(), params, d_out3)
+    torch.cuda.synchronize()
+    assert np.abs(d_out3.cpu().numpy() - want[2:4]).max() <= TOL
     assert eng.hybrid_tiles == 0
     eng.close()
