@@ -141,6 +141,7 @@ extern "C" int dsrg_annotation_forward_dev(dsrg_engine *h, int B, const int32_t 
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     return annotation_forward(e, B, tag_offsets, tags, cue_offsets, cue_idx, flip, images_in_dev, Hi, Wi,
                               labels_out_dev, cues_out_dev, images_out_dev, (cudaStream_t)stream);
 }
@@ -155,6 +156,7 @@ extern "C" int dsrg_annotation_forward_host(dsrg_engine *h, int B, const int32_t
     if (rc) return rc;
     if ((rc = ensure_staging(e))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     float *d_in = nullptr, *d_out = nullptr;
     const size_t nimg = images_out ? (size_t)B * 3 * Hi * Wi : 0;
     if (images_out) {

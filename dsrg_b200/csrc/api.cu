@@ -416,6 +416,7 @@ dsrg_engine *dsrg_engine_create(int device, int max_batch, int H, int W, int M) 
     if (!rc && cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaEventCreateWithFlags(&e->fork_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
     if (!rc && cudaEventCreateWithFlags(&e->join_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
+    if (!rc && cudaEventCreateWithFlags(&e->order_event, cudaEventDisableTiming) != cudaSuccess) rc = DSRG_E_CUDA;
     if (const char *ev = getenv("DSRG_B200_LANES")) e->lanes = atoi(ev) == 2 ? 2 : 1;
     if (const char *ev = getenv("DSRG_B200_WIRE")) e->wire_compress = atoi(ev) != 0;
     if (const char *ev = getenv("DSRG_B200_GRAPHS")) e->use_graphs = atoi(ev) != 0;
@@ -446,6 +447,7 @@ void dsrg_engine_destroy(dsrg_engine *h) {
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     if (e->fork_event) cudaEventDestroy(e->fork_event);
     if (e->join_event) cudaEventDestroy(e->join_event);
+    if (e->order_event) cudaEventDestroy(e->order_event);
     if (e->out_stream) cudaStreamDestroy(e->out_stream);
     for (auto ev : e->pipe_events) cudaEventDestroy(ev);
     wire_free(e);
@@ -587,6 +589,7 @@ int dsrg_crf_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_layo
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     if (!out || (out_layout != DSRG_LAYOUT_NHWC && out_layout != DSRG_LAYOUT_NCHW)) {
         set_error("bad output argument");
         return DSRG_E_INVALID;
@@ -615,6 +618,7 @@ int dsrg_crf_map_batch_dev(dsrg_engine *h, int B, const float *unary, int unary_
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     if (!labels_out) {
         set_error("labels_out is NULL");
         return DSRG_E_INVALID;
@@ -642,6 +646,7 @@ int dsrg_crf_batch_host(dsrg_engine *h, int B, const float *unary, int unary_lay
     }
     if ((rc = ensure_staging(e))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     const size_t n = (size_t)B * e->M * e->N;
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, unary, n * sizeof(float), cudaMemcpyHostToDevice, s));
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image, image, (size_t)B * e->N * 3, cudaMemcpyHostToDevice, s));
@@ -658,6 +663,7 @@ int dsrg_srg_batch_dev(dsrg_engine *h, int B, const float *labels, const float *
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     if (!labels || !probs || !cues || !seeds_out) {
         set_error("NULL pointer argument");
         return DSRG_E_INVALID;
@@ -699,6 +705,7 @@ int dsrg_dsrg_forward_dev(dsrg_engine *h, int B, const float *labels, float *pro
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     if (!labels || !probs || !cues || !seeds_out) {
         set_error("NULL pointer argument");
         return DSRG_E_INVALID;
@@ -714,6 +721,7 @@ int dsrg_crflayer_forward_dev(dsrg_engine *h, int B, float *probs, const uint8_t
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     if (!probs || !log_out) {
         set_error("NULL pointer argument");
         return DSRG_E_INVALID;
@@ -745,6 +753,7 @@ int dsrg_srg_last_crf_host(dsrg_engine *h, int B, const float *labels, const flo
     }
     if ((rc = ensure_staging(e))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     const size_t n = (size_t)B * e->M * e->N;
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_labels, labels, (size_t)B * e->M * sizeof(float), cudaMemcpyHostToDevice, s));
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, cues, n * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -769,6 +778,7 @@ int dsrg_crf_last_marginals_host(dsrg_engine *h, int B, float *out, int out_layo
     }
     if ((rc = ensure_staging(e))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     if ((rc = meanfield_export(e, B, e->st_out, out_layout, s))) return rc;
     DSRG_CUDA_TRY(cudaMemcpyAsync(out, e->st_out, (size_t)B * e->M * e->N * sizeof(float), cudaMemcpyDeviceToHost, s));
     DSRG_CUDA_TRY(cudaStreamSynchronize(s));
@@ -787,6 +797,7 @@ int dsrg_crflayer_forward_host(dsrg_engine *h, int B, float *probs, const uint8_
     }
     if ((rc = ensure_staging(e))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     const size_t n = (size_t)B * e->M * e->N;
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_image, image, (size_t)B * e->N * 3, cudaMemcpyHostToDevice, s));
@@ -810,6 +821,7 @@ int dsrg_seedloss_forward_host(dsrg_engine *h, int B, const float *probs, const 
     }
     if ((rc = ensure_staging(e))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     const size_t n = (size_t)B * e->M * e->N;
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, seeds, n * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -831,6 +843,7 @@ int dsrg_seedloss_backward_host(dsrg_engine *h, int B, int n_global, const float
     }
     if ((rc = ensure_staging(e))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     const size_t n = (size_t)B * e->M * e->N;
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, probs, n * sizeof(float), cudaMemcpyHostToDevice, s));
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, seeds, n * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -846,6 +859,7 @@ int dsrg_seedloss_forward_dev(dsrg_engine *h, int B, const float *probs, const f
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     if (!probs || !seeds || !terms_out) {
         set_error("NULL pointer argument");
         return DSRG_E_INVALID;
@@ -859,6 +873,7 @@ int dsrg_seedloss_backward_dev(dsrg_engine *h, int B, int n_global, const float 
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     if (!probs || !seeds || !grad || n_global < 1) {
         set_error("bad argument");
         return DSRG_E_INVALID;
@@ -1012,6 +1027,7 @@ static int densecrf_run(dsrg_densecrf *c, int n_iters, Engine **eng) {
     if (!c->has_unary) c->unary.assign((size_t)c->W * c->H * c->M, 0.0f);  // unary.fill(0), densecrf.cpp:117
     c->params.n_iters = n_iters;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, c->unary.data(), c->unary.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     if (!c->has_pairwise) {
         // no pairwise term: every mean-field step reproduces Q = softmax(-unary) (densecrf.cpp:120-128 with an
@@ -1043,6 +1059,7 @@ int dsrg_densecrf_inference(dsrg_densecrf *c, int n_iters, float *probs_out) {
     if (rc) return rc;
     DeviceScope dev_scope(e);
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     if ((rc = meanfield_export(e, 1, e->st_out, DSRG_LAYOUT_NHWC, s))) return rc;
     DSRG_CUDA_TRY(cudaMemcpyAsync(probs_out, e->st_out, c->unary.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
     return check_device_flag(e, s);
@@ -1059,6 +1076,7 @@ int dsrg_densecrf_map(dsrg_densecrf *c, int n_iters, int *labels) {
     if (rc) return rc;
     DeviceScope dev_scope(e);
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     if ((rc = meanfield_export_map(e, 1, e->st_lmap, s))) return rc;
     DSRG_CUDA_TRY(cudaMemcpyAsync(labels, e->st_lmap, (size_t)c->W * c->H * sizeof(int), cudaMemcpyDeviceToHost, s));
     return check_device_flag(e, s);

@@ -200,6 +200,10 @@ struct Engine {
     int32_t *st_lmap = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr, aux_stream = nullptr;
     cudaEvent_t fork_event = nullptr, join_event = nullptr;
+    // order of the passes of this engine across streams (StreamScope)
+    cudaEvent_t order_event = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
     int lanes = 1;  // 2 = run the mean-field loop as two half-batches on two streams (measured: +1 %, off)
     std::vector<cudaEvent_t> pipe_events;
     int host_chunk = 0;   // > 0 caps the images per pipeline stage of the *_host entry points
@@ -219,6 +223,37 @@ struct Engine {
     struct ProfRec { int tag; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
+};
+
+// An engine is one set of buffers: two passes must not overlap.  Passes issued on ONE stream are ordered by it;
+// when a caller moves to another stream (torch side streams are non-blocking: not even the legacy default stream
+// orders them) the new pass first waits for the event the previous pass left behind.  Costs one cudaEventRecord
+// per entry point.  Inside the caller's own stream capture nothing is recorded or awaited.
+struct StreamScope {
+    Engine *e;
+    cudaStream_t s;
+    bool live = false;
+    StreamScope(Engine *e_, cudaStream_t s_) : e(e_), s(s_) {
+        if (!e || !e->order_event) return;
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        if (st != cudaStreamCaptureStatusNone) return;
+        live = true;
+        if (e->last_stream_valid && e->last_stream != s && cudaStreamWaitEvent(s, e->order_event, 0) != cudaSuccess)
+            cudaGetLastError();
+    }
+    ~StreamScope() {
+        if (!live) return;
+        if (cudaEventRecord(e->order_event, s) == cudaSuccess) {
+            e->last_stream = s;
+            e->last_stream_valid = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
 };
 
 inline bool hybrid_tiles_on(const Engine *e, int B) {

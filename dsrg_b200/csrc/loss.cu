@@ -296,6 +296,7 @@ static int host_elementwise(dsrg_engine *h, int B, const float *in0, const float
     }
     if ((rc = ensure_staging(e))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     const size_t n = (size_t)B * e->M * e->N;
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, in0, n * sizeof(float), cudaMemcpyHostToDevice, s));
     if (in1) DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_cues, in1, n * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -318,28 +319,36 @@ int dsrg_softmax_forward_dev(dsrg_engine *h, int B, const float *preds, float *p
     Engine *e = (Engine *)h;
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
-    return rc ? rc : softmax_forward(e, B, preds, probs_out, (cudaStream_t)stream);
+    if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
+    return softmax_forward(e, B, preds, probs_out, (cudaStream_t)stream);
 }
 int dsrg_softmax_backward_dev(dsrg_engine *h, int B, const float *preds, const float *top_diff, float *grad_out,
                               void *stream) {
     Engine *e = (Engine *)h;
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
-    return rc ? rc : softmax_backward(e, B, preds, top_diff, grad_out, (cudaStream_t)stream);
+    if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
+    return softmax_backward(e, B, preds, top_diff, grad_out, (cudaStream_t)stream);
 }
 int dsrg_constrainloss_forward_dev(dsrg_engine *h, int B, const float *probs, const float *log_smooth,
                                    float *loss_out, void *stream) {
     Engine *e = (Engine *)h;
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
-    return rc ? rc : constrain_forward(e, B, probs, log_smooth, loss_out, (cudaStream_t)stream);
+    if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
+    return constrain_forward(e, B, probs, log_smooth, loss_out, (cudaStream_t)stream);
 }
 int dsrg_constrainloss_backward_dev(dsrg_engine *h, int B, const float *probs, const float *log_smooth,
                                     float *grad_probs, float *grad_log, void *stream) {
     Engine *e = (Engine *)h;
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
-    return rc ? rc : constrain_backward(e, B, probs, log_smooth, grad_probs, grad_log, (cudaStream_t)stream);
+    if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
+    return constrain_backward(e, B, probs, log_smooth, grad_probs, grad_log, (cudaStream_t)stream);
 }
 int dsrg_softmax_forward_host(dsrg_engine *h, int B, const float *preds, float *probs_out) {
     return host_elementwise(h, B, preds, nullptr, probs_out, nullptr, nullptr, 0);

@@ -221,6 +221,7 @@ extern "C" int dsrg_zoom_scores_dev(dsrg_engine *h, const float *scores_dev, int
     DeviceScope dev_scope(e);
     int rc = check_batch(e, 1);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     if (!scores_dev || !out_dev || hi < 1 || wi < 1) {
         set_error("bad argument");
         return DSRG_E_INVALID;
@@ -242,6 +243,7 @@ extern "C" int dsrg_zoom_scores_host(dsrg_engine *h, const float *scores, int hi
     const size_t nin = (size_t)e->M * hi * wi, nout = (size_t)e->N * e->M;
     if ((rc = grow_raw(e, nin))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_raw, scores, nin * sizeof(float), cudaMemcpyHostToDevice, s));
     if (accumulate)
         DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_unary, out, nout * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -259,6 +261,7 @@ extern "C" int dsrg_predict_mask_dev(dsrg_engine *h, int mode, int n_scales, con
     DeviceScope dev_scope(e);
     int rc = check_batch(e, 1);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     return predict_mask(e, mode, n_scales, scores_dev, hs, ws, image_dev, eps, smooth, params, labels_sel, n_sel,
                         result_out_dev, probs_out_dev, (cudaStream_t)stream);
 }
@@ -286,6 +289,7 @@ extern "C" int dsrg_predict_mask_host(dsrg_engine *h, int mode, int n_scales, co
     }
     if ((rc = grow_raw(e, total))) return rc;
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     const float *dptr[16];
     size_t at = 0;
     for (int k = 0; k < n_scales; k++) {

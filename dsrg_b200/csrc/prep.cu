@@ -47,6 +47,7 @@ extern "C" int dsrg_prepare_image_dev(dsrg_engine *h, int B, int Hi, int Wi, con
     DeviceScope dev_scope(e);
     int rc = check_batch(e, B);
     if (rc) return rc;
+    StreamScope stream_scope(e, (cudaStream_t)stream);
     if (!images_dev || !mean_pixel || !image_out_dev || Hi < 1 || Wi < 1) {
         set_error("bad argument");
         return DSRG_E_INVALID;
@@ -74,6 +75,7 @@ extern "C" int dsrg_prepare_image_host(dsrg_engine *h, int B, int Hi, int Wi, co
         e->st_raw_cap = need;
     }
     cudaStream_t s = e->own_stream;
+    StreamScope stream_scope(e, s);
     DSRG_CUDA_TRY(cudaMemcpyAsync(e->st_raw, images, need * sizeof(float), cudaMemcpyHostToDevice, s));
     if ((rc = prepare_image(e, B, Hi, Wi, e->st_raw, mean_pixel, e->st_image, s))) return rc;
     DSRG_CUDA_TRY(cudaMemcpyAsync(image_out, e->st_image, (size_t)B * e->N * 3, cudaMemcpyDeviceToHost, s));

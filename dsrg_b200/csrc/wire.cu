@@ -307,6 +307,7 @@ static int host_pass_impl(dsrg_engine *h, int B, const float *labels, float *pro
         e->pipe_events.push_back(ev);
     }
     cudaStream_t s_in = e->in_stream, s = e->own_stream, s_out = e->out_stream;
+    StreamScope stream_scope(e, s);
     const size_t img_elems = (size_t)e->M * e->N;
     const int n_img = (int)img_elems;
     const size_t wpi = (img_elems + 31) / 32;

@@ -196,7 +196,10 @@ def test_srg_adversarial_connectivity(torch_cuda):
 def test_graph_replay_matches_plain_launches(torch_cuda):
     """Repeated device passes are replayed as CUDA graphs (csrc/graph.cu): same seeds bit for bit, marginals within
     the atomics' run-to-run noise, replays really happen on a side stream and never on the legacy default stream,
-    and a call with other arguments in between does not disturb a cached graph."""
+    and a call with other arguments in between does not disturb a cached graph.  The test moves from the legacy
+    default stream to a non-blocking side stream WITHOUT synchronising: the engine orders its own passes across
+    streams (StreamScope, csrc/common.cuh) -- before it did, the side stream's first pass could overlap the tail of
+    the default stream's and this test failed once in a few runs with garbage marginals."""
     torch = torch_cuda
     B, H, W, M = 3, 41, 41, 21
     batch = synth.make_batch(B, H, W, cues="cam", image="smooth", start=40)
