@@ -1,11 +1,15 @@
 """Turn gpurun_out/ captures into the tracked summaries under profiles/.
 
-usage: python tools/make_profiles.py <tag> <bench.json> <launches.csv> <prof.ncu-rep> [<ref.json>]
+usage: python tools/make_profiles.py <tag> <bench.json> <launches.csv> <prof.ncu-rep> [<ref.json>] [name=<other.ncu-rep> ...]
+(every name=<rep> adds profiles/<tag>_ncu_full_<name>.csv with the same headline metrics)
 """
 import collections, csv, json, os, subprocess, sys
 csv.field_size_limit(10**9)
 tag, bench, launches, rep = sys.argv[1:5]
-ref = sys.argv[5] if len(sys.argv) > 5 else None
+rest = sys.argv[5:]
+extra_reps = [a.split("=", 1) for a in rest if "=" in a]
+rest = [a for a in rest if "=" not in a]
+ref = rest[0] if rest else None
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
 os.makedirs(out, exist_ok=True)
 
@@ -39,7 +43,7 @@ with open(os.path.join(out, "%s_launches.csv" % tag), "w") as f:
     for r in raw:
         f.write("%s,%s,%.2f\n" % r)
 lines = ["| kernel | launches | total µs | avg µs | share (ncu) | share (bench events) |", "|---|---|---|---|---|---|"]
-tagmap = {"k_mf_tile": "mf_tile", "k_mf_blur": None, "k_lattice_insert": "lattice_insert", "k_srg_label": "srg_label",
+tagmap = {"k_mf_tile<": "mf_tile", "k_mf_tile_hy": "mf_tile_hybrid", "k_mf_blur": None, "k_lattice_insert": "lattice_insert", "k_srg_label": "srg_label",
           "k_srg_emit": "srg_emit", "k_srg_merge": "srg_merge", "k_srg_flag": "srg_flag", "k_mf_zero": "mf_zero"}
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     ev = ""
@@ -49,29 +53,36 @@ for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append("| `%s` | %d | %.1f | %.1f | %.1f %% | %s |" % (k, n, t, t / n, 100 * t / tot, ev))
 
 # 3. ncu --set full headline metrics per captured kernel
-rawcsv = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(rawcsv.splitlines()))
-h, units = rr[0], rr[1]
-want = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
-        "launch__occupancy_limit_shared_mem", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
-stalls = [x for x in h if x.startswith("smsp__average_warps_issue_stalled_") and x.endswith("_per_issue_active.ratio")]
-seen = {}
-with open(os.path.join(out, "%s_ncu_full.csv" % tag), "w") as f:
-    f.write("kernel," + ",".join(want) + ",top_stalls\n")
-    for r in rr[2:]:
-        name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").replace("dsrg::", "")
-        key = name
-        if seen.get(key, 0) >= 2:
-            continue
-        seen[key] = seen.get(key, 0) + 1
-        vals = [r[h.index(w)] + " " + units[h.index(w)] if w in h else "" for w in want]
-        st = sorted(((float(r[h.index(x)]), x.split("stalled_")[1].split("_per_issue")[0]) for x in stalls), reverse=True)[:5]
-        f.write('"%s",' % name + ",".join('"%s"' % v for v in vals) + ',"' + " ".join("%s=%.2f" % (n, v) for v, n in st) + '"\n')
+def ncu_headlines(rep, dest):
+    rawcsv = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(rawcsv.splitlines()))
+    h, units = rr[0], rr[1]
+    want = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+            "launch__occupancy_limit_shared_mem", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+            "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum"]
+    stalls = [x for x in h if x.startswith("smsp__average_warps_issue_stalled_") and x.endswith("_per_issue_active.ratio")]
+    seen = {}
+    with open(dest, "w") as f:
+        f.write("kernel," + ",".join(want) + ",top_stalls\n")
+        for r in rr[2:]:
+            name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").replace("dsrg::", "")
+            key = name
+            if seen.get(key, 0) >= 2:
+                continue
+            seen[key] = seen.get(key, 0) + 1
+            vals = [r[h.index(w)] + " " + units[h.index(w)] if w in h else "" for w in want]
+            st = sorted(((float(r[h.index(x)]), x.split("stalled_")[1].split("_per_issue")[0]) for x in stalls), reverse=True)[:5]
+            f.write('"%s",' % name + ",".join('"%s"' % v for v in vals) + ',"' + " ".join("%s=%.2f" % (n, v) for v, n in st) + '"\n')
+
+
+ncu_headlines(rep, os.path.join(out, "%s_ncu_full.csv" % tag))
+for name, path in extra_reps:
+    ncu_headlines(path, os.path.join(out, "%s_ncu_full_%s.csv" % (tag, name)))
 
 with open(os.path.join(out, "%s_summary.md" % tag), "w") as f:
     f.write("# profile %s\n\n" % tag)
