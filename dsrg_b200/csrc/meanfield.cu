@@ -538,6 +538,9 @@ k_mf_tile_hy(const float *U, float *U_rw, int clamp, float *__restrict__ Qout, T
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
+        // the previous tile of this CTA wrote its Q rows into the same shared memory through the generic proxy: order
+        // those writes before the bulk copies (async proxy) of this tile
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int i = tid; i < n_sp + n_bi; i += kTileThreads) {
             const bool is_sp = i < n_sp;
             const int lv = is_sp ? i : i - n_sp;
