@@ -57,13 +57,13 @@ struct Lattice {
     // tile-local view (32x8-pixel tiles): the distinct vertices a tile touches, so that splat and
     // slice run out of shared memory (see tiles.cu)
     int maxloc = 0;                // local-vertex capacity per tile (kMaxLocSp / kMaxLocHy)
-    int32_t *tl_nloc = nullptr;    // [nimg][ntiles] local vertices of the tile | kTileHybrid if other incidences go direct
+    int32_t *tl_nloc = nullptr;    // [nimg][ntiles] local vertices of the tile; | kTileHybrid: hybrid tile; -1: overflow tile without a list
     uint8_t *tl_hy = nullptr;      // [nimg][ntiles] 1: hybrid tile, k_mf_tile skips it (bilateral only)
     int2 *tl_hdr = nullptr;        // [nimg][ntiles][maxloc] per local vertex: (first entry | count<<16, local row id)
     int2 *tl_pack = nullptr;       // [nimg][ntiles][entcap] CSR entries grouped by local vertex:
                                    // (byte offset of the pixel's Q row in the tile, weight bits)
     int entcap = 0;                // 256*(d+1) + 2
-    uint16_t *tl_loc = nullptr;    // [nimg][d+1][N] local vertex index of (pixel, r)
+    uint16_t *tl_loc = nullptr;    // [nimg][d+1][N] local vertex index of (pixel, r), kLocRemote if not in the tile's list
     float *wn = nullptr;           // [nimg][d+1][N] barycentric weight * norm
     float scale[5] = {0, 0, 0, 0, 0};  // elevation scale factors (permutohedral.cpp:179-182)
     float sigma[5] = {0, 0, 0, 0, 0};  // feature sigmas: x, y[, c0, c1, c2]

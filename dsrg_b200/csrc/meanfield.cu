@@ -73,10 +73,12 @@ k_mf_init(const float *unary, float *unary_rw, int layout, int clamp, float *U, 
 // by local vertex) so that each distinct vertex receives ONE vectorised global reduction
 // (REDG.ADD.F32x4) per tile instead of one scalar atomic per pixel, vertex and label.
 // norm is folded into the weights (wn = bary*norm, built in tiles.cu).
-// Tiles that touch more distinct vertices than fit (noise images) take the direct global path.
+// Tiles that touch more distinct vertices than fit take the direct global path (count -1: uniform noise, sigma/12
+// lattices) or, when a few vertices carry most of their incidences (textured images), are hybrid tiles and belong to
+// k_mf_tile_hy below (tiles.cu decides).
 // ---------------------------------------------------------------------------------------------
 struct TileLat {
-    // direct (fallback) view
+    // direct view (overflow tiles, remote incidences of hybrid tiles)
     const int32_t *off;      // [nimg][dp1][N] local row (1-based)
     const int32_t *rowbase;  // [B+1]
     // tile-local view (tiles.cu)
