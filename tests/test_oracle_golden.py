@@ -177,7 +177,7 @@ def test_crf_oracle_is_bit_exact_vs_the_reference_build(name):
 
 @needs_ref_crf
 @pytest.mark.parametrize("H,W,M,sf,img", [(97, 131, 21, 1.0, "smooth"), (60, 45, 5, 12.0, "noise"), (33, 33, 2, 1.0, "noise"),
-                                          (161, 161, 21, 1.0, "smooth")])
+                                          (161, 161, 21, 1.0, "smooth"), (120, 90, 21, 1.0, "photo")])
 def test_crf_oracle_vs_reference_build_other_shapes(H, W, M, sf, img):
     """incl. M = 2, where Permutohedral::compute takes the seqCompute branch (permutohedral.cpp:600-601)."""
     rng = np.random.RandomState(H * 7 + M)
